@@ -1,0 +1,71 @@
+// clpt_device.cuh -- device-side data layout and launch interface (internal).
+//
+// HBM layout produced by CLSetMeshes (scene_pack.cpp) from the reference's wire
+// format (68-byte packed nodes + tri_indices -> tris -> verts indirection,
+// include/kd_tree.h:31-50, src/kernel.cl:333-340):
+//
+//   nodes   uint2[n_nodes]   8 B per node, siblings adjacent
+//             split: x = float bits of the plane, y = (first_child << 2) | axis
+//                    children are first_child (p <= plane) and first_child+1
+//             leaf : x = leaf record index,        y = 3
+//   leaves  float4[4*n_leaves]  64 B per leaf, 64-byte aligned
+//             [0] = min.xyz, int bits of the first triangle slot
+//             [1] = max.xyz, int bits of the triangle count
+//             [2] = ropes 0..3 (int bits; node index in `nodes`, -1 = outside)
+//             [3] = ropes 4..5, 0, 0
+//   tri     float4[3*n_refs]    48 B per leaf triangle slot, in leaf order, so a
+//                               leaf's triangles are one contiguous run
+//             [0] = v0.xyz, int bits of the primitive id
+//             [1] = v1 - v0 (fp32, same rounding as kernel.cl:235)
+//             [2] = v2 - v0
+//   corners int4[3*n_prims], norms float4[]: as uploaded, only read when
+//             shading a hit with vertex normals (once per ray)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct ClptMaterial {
+    float albedo[3];
+    int kind;
+    float emission[3];
+    float pad;
+};
+
+struct ClptScene {
+    const uint2 *nodes;
+    const float4 *leaves;
+    const float4 *tri;
+    const int4 *corners;
+    const float4 *norms;
+    const int *tri_material;
+    const ClptMaterial *materials;
+    int n_materials;
+    int n_nodes, n_leaves, n_refs, n_prims, n_norms;
+    float root_min[3], root_max[3];
+};
+
+struct ClptFrame {
+    float cam[16]; // row-major inverse camera matrix
+    int width, height;
+    int mode, depth, spp, flags;
+    unsigned int seed, sample_base;
+    int max_leaf_visits;
+    int rank, nranks, tile_rows; // row-tile sharding; nranks == 1 -> whole image
+    int local_rows;              // rows this rank renders (slab height)
+    float4 *target;              // slab (nranks > 1) or the image itself
+    int *aov_prim;               // full-image indexed, may be null
+    float *aov_t;
+    float2 *aov_uv;
+    unsigned long long *counters; // 6 counters, may be null
+};
+
+enum { CLPT_F_JITTER = 1, CLPT_F_ACCUMULATE = 2, CLPT_F_COUNTERS = 4 };
+
+// render_kernel.cu
+void clpt_launch_render(const ClptScene &scene, const ClptFrame &frame, cudaStream_t stream);
+void clpt_launch_deinterleave(const float4 *gathered, float4 *image, int width, int height,
+                              int nranks, int tile_rows, int slab_rows, cudaStream_t stream);
+void clpt_launch_fill(float4 *dst, size_t n, float value, cudaStream_t stream);
+void clpt_launch_normalise(const float4 *src, float4 *dst, size_t n, cudaStream_t stream);
+const void *clpt_render_kernel_symbol(void);

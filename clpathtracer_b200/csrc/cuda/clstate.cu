@@ -1,0 +1,641 @@
+// clstate.cu -- the CLState.h boundary on top of the CUDA runtime.
+//
+// Mirrors the reference's render-state layer (src/CLState.c): a file-static
+// singleton that owns the device buffers, takes the scene and camera from the
+// host, and launches one frame per CLExecute.  Every call is synchronous and
+// any failure is fatal, as in the reference (src/error.c:147-154).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "CLHandler.h"
+#include "CLState.h"
+#include "clpt_device.cuh"
+#include "clpt_host.h"
+#include "scene_pack.h"
+
+#define CU(call) handle_err((int)(call), __FILE__, __LINE__)
+
+namespace {
+
+[[noreturn]] void fatal(const char *file, int line, const char *what) {
+    fprintf(stderr, "%s:%d: CLState Error: %s\n", file, line, what);
+    exit(EXIT_FAILURE);
+}
+#define FATAL(msg) fatal(__FILE__, __LINE__, (msg))
+
+// ---- NCCL, resolved at run time so the library loads on a box without it ----
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+void nccl_load() {
+    if (g_nccl.lib) return;
+    const char *names[] = { "libnccl.so.2", "libnccl.so" };
+    for (const char *n : names) {
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) FATAL("NCCL is required for multi-GPU rendering but libnccl.so.2 could not be loaded");
+    auto sym = [](const char *name) {
+        void *p = dlsym(g_nccl.lib, name);
+        if (!p) {
+            fprintf(stderr, "missing NCCL symbol %s\n", name);
+            exit(EXIT_FAILURE);
+        }
+        return p;
+    };
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))sym("ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))sym("ncclCommInitRank");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))sym("ncclAllGather");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))sym("ncclCommDestroy");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))sym("ncclGetErrorString");
+}
+
+void nccl_check(ncclResult_t r, const char *file, int line) {
+    if (r == ncclSuccess) return;
+    fprintf(stderr, "%s:%d: NCCL Error: %s\n", file, line,
+            g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "unknown");
+    exit(EXIT_FAILURE);
+}
+#define NC(call) nccl_check((call), __FILE__, __LINE__)
+
+template <typename T>
+struct DevBuf {
+    T *ptr = nullptr;
+    size_t count = 0;
+    void release() {
+        if (ptr) CU(cudaFree(ptr));
+        ptr = nullptr;
+        count = 0;
+    }
+    // exact-size re-creation, like resize_buffer (src/CLState.c:92-102)
+    void resize(size_t n) {
+        release();
+        if (n) CU(cudaMalloc((void **)&ptr, n * sizeof(T)));
+        count = n;
+    }
+    void upload(const T *src, size_t n, cudaStream_t s) {
+        resize(n);
+        if (n) {
+            CU(cudaMemcpyAsync(ptr, src, n * sizeof(T), cudaMemcpyHostToDevice, s));
+            CU(cudaStreamSynchronize(s));
+        }
+    }
+};
+
+struct {
+    bool inited = false;
+    int device = -1; // -1: take $CLPT_DEVICE or 0
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    cudaEvent_t ev_user[8] = {};
+
+    kd host_kd = { nullptr, nullptr, nullptr, nullptr, nullptr };
+    bool owns_kd = false;
+
+    DevBuf<uint2> nodes;
+    DevBuf<float4> leaves, tri, norms;
+    DevBuf<int4> corners;
+    DevBuf<unsigned char> objects;
+    int objcount = 0;
+    DevBuf<ClptMaterial> materials;
+    DevBuf<int> tri_material;
+    ClptScene scene = {};
+    bool have_scene = false;
+
+    float cam[16] = { 0 };
+
+    int mode = CLPT_MODE_NORMAL, depth = 2, spp = 1, flags = 0; // depth 2: src/kernel.cl:468
+    unsigned seed = 0, sample_base = 0;
+    int max_leaf_visits = 4096;
+
+    int width = 0, height = 0;
+    bool headless = false, have_image = false;
+    DevBuf<float4> image, slab, gathered, scratch;
+    bool aov = false;
+    DevBuf<int> aov_prim;
+    DevBuf<float> aov_t;
+    DevBuf<float2> aov_uv;
+    DevBuf<unsigned long long> counters;
+    unsigned long long host_counters[6] = { 0 };
+    float last_kernel_ms = 0;
+    int last_launches = 0;
+    DevBuf<unsigned char> l2_flush;
+
+    int rank = 0, nranks = 1, tile_rows = 8;
+    ncclComm_t comm = nullptr;
+} St;
+
+void require_init(const char *who) {
+    if (!St.inited) {
+        fprintf(stderr, "%s: CLInit has not been called\n", who);
+        exit(EXIT_FAILURE);
+    }
+}
+
+int slab_rows_for(int height) {
+    const int tiles = (height + St.tile_rows - 1) / St.tile_rows;
+    const int per_rank = (tiles + St.nranks - 1) / St.nranks;
+    return per_rank * St.tile_rows;
+}
+
+int local_rows_for(int height) {
+    // rows of the slab that map to real image rows for this rank
+    const int tiles = (height + St.tile_rows - 1) / St.tile_rows;
+    int mine = 0;
+    for (int t = St.rank; t < tiles; t += St.nranks) mine++;
+    return mine * St.tile_rows;
+}
+
+void rebuild_scene_struct() {
+    ClptScene &S = St.scene;
+    S.nodes = St.nodes.ptr;
+    S.leaves = St.leaves.ptr;
+    S.tri = St.tri.ptr;
+    S.corners = St.corners.ptr;
+    S.norms = St.norms.ptr;
+    S.tri_material = St.tri_material.ptr;
+    S.materials = St.materials.ptr;
+    S.n_materials = (int)St.materials.count;
+    S.n_norms = (int)St.norms.count;
+}
+
+void upload_scene(const kdnode *nodes, size_t node_bytes, const int *tri_indices, size_t tri_index_bytes,
+                  const cl_int3 *tris, size_t tri_bytes, const Vector4 *verts, size_t vert_bytes,
+                  const Vector4 *norms, size_t norm_bytes) {
+    ClptPackedScene packed;
+    std::string err;
+    const size_t n_norms = norms ? norm_bytes / sizeof(Vector4) : 0;
+    if (!clpt_pack_scene(nodes, node_bytes / sizeof(kdnode), tri_indices, tri_index_bytes / sizeof(int), tris,
+                         tri_bytes / sizeof(cl_int3), verts, vert_bytes / sizeof(Vector4), n_norms, packed,
+                         err)) {
+        fprintf(stderr, "CLSetMeshes: invalid scene: %s\n", err.c_str());
+        exit(EXIT_FAILURE);
+    }
+    St.nodes.upload(reinterpret_cast<const uint2 *>(packed.nodes.data()), packed.nodes.size(), St.stream);
+    St.leaves.upload(reinterpret_cast<const float4 *>(packed.leaves.data()), packed.leaves.size(), St.stream);
+    St.tri.upload(reinterpret_cast<const float4 *>(packed.tri.data()), packed.tri.size(), St.stream);
+    St.corners.upload(reinterpret_cast<const int4 *>(tris), tri_bytes / sizeof(cl_int3), St.stream);
+    if (n_norms) {
+        St.norms.upload(reinterpret_cast<const float4 *>(norms), n_norms, St.stream);
+    } else {
+        St.norms.release(); // the reference keeps a stale buffer here (src/CLState.c:146); unused either way
+    }
+    // per-triangle materials belong to the previous mesh
+    St.tri_material.release();
+    ClptScene &S = St.scene;
+    S.n_nodes = packed.n_nodes;
+    S.n_leaves = packed.n_leaves;
+    S.n_refs = packed.n_refs;
+    S.n_prims = packed.n_prims;
+    for (int a = 0; a < 3; a++) {
+        S.root_min[a] = packed.root_min[a];
+        S.root_max[a] = packed.root_max[a];
+    }
+    rebuild_scene_struct();
+    St.have_scene = true;
+}
+
+void release_host_kd() {
+    if (St.owns_kd) delete_kd(St.host_kd);
+    St.host_kd = kd{ nullptr, nullptr, nullptr, nullptr, nullptr };
+    St.owns_kd = false;
+}
+
+void alloc_targets() {
+    const size_t px = (size_t)St.width * St.height;
+    St.image.resize(px);
+    clpt_launch_fill(St.image.ptr, px, 0.0f, St.stream);
+    if (St.nranks > 1) {
+        const size_t slab_px = (size_t)slab_rows_for(St.height) * St.width;
+        St.slab.resize(slab_px);
+        clpt_launch_fill(St.slab.ptr, slab_px, 0.0f, St.stream);
+        if (St.comm) St.gathered.resize(slab_px * St.nranks);
+    } else {
+        St.slab.release();
+        St.gathered.release();
+    }
+    if (St.aov) {
+        St.aov_prim.resize(px);
+        St.aov_t.resize(px);
+        St.aov_uv.resize(px);
+        CU(cudaMemsetAsync(St.aov_prim.ptr, 0xff, px * sizeof(int), St.stream));
+        CU(cudaMemsetAsync(St.aov_t.ptr, 0, px * sizeof(float), St.stream));
+        CU(cudaMemsetAsync(St.aov_uv.ptr, 0, px * sizeof(float2), St.stream));
+    }
+    St.scratch.release();
+    St.sample_base = 0;
+    CU(cudaStreamSynchronize(St.stream));
+}
+
+} // namespace
+
+// Internal: the frame launch, shared by CLExecute and CLEnqueueKernel.
+void clpt_state_launch_frame(int width, int height) {
+    require_init("CLExecute");
+    if (!St.have_image) FATAL("no render target: call CLCreateImage or CLCreateImageHeadless first");
+    if (width != St.width || height != St.height) {
+        fprintf(stderr, "CLExecute: launch size %dx%d does not match the %dx%d render target\n", width, height,
+                St.width, St.height);
+        exit(EXIT_FAILURE);
+    }
+    if (!St.have_scene) FATAL("no scene: call CLSetMeshes first");
+    St.last_launches = 0;
+
+    ClptFrame F;
+    memcpy(F.cam, St.cam, sizeof(F.cam));
+    F.width = width;
+    F.height = height;
+    F.mode = St.mode;
+    F.depth = St.depth;
+    F.spp = St.spp;
+    F.flags = St.flags;
+    F.seed = St.seed;
+    F.sample_base = St.sample_base;
+    F.max_leaf_visits = St.max_leaf_visits;
+    F.rank = St.rank;
+    F.nranks = St.nranks;
+    F.tile_rows = St.tile_rows;
+    F.local_rows = St.nranks > 1 ? local_rows_for(height) : height;
+    F.target = St.nranks > 1 ? St.slab.ptr : St.image.ptr;
+    F.aov_prim = St.aov ? St.aov_prim.ptr : nullptr;
+    F.aov_t = St.aov ? St.aov_t.ptr : nullptr;
+    F.aov_uv = St.aov ? St.aov_uv.ptr : nullptr;
+    F.counters = nullptr;
+    if (St.flags & CLPT_FLAG_COUNTERS) {
+        if (!St.counters.ptr) St.counters.resize(6);
+        CU(cudaMemsetAsync(St.counters.ptr, 0, 6 * sizeof(unsigned long long), St.stream));
+        F.counters = St.counters.ptr;
+    }
+
+    CU(cudaEventRecord(St.ev_start, St.stream));
+    clpt_launch_render(St.scene, F, St.stream);
+    CU(cudaGetLastError());
+    St.last_launches++;
+    CU(cudaEventRecord(St.ev_stop, St.stream));
+
+    if (St.nranks > 1 && St.comm) {
+        const size_t slab_px = (size_t)slab_rows_for(height) * width;
+        NC(g_nccl.AllGather(St.slab.ptr, St.gathered.ptr, slab_px * 4, ncclFloat, St.comm, St.stream));
+        clpt_launch_deinterleave(St.gathered.ptr, St.image.ptr, width, height, St.nranks, St.tile_rows,
+                                 slab_rows_for(height), St.stream);
+        CU(cudaGetLastError());
+        St.last_launches++;
+    } else if (St.nranks > 1) {
+        // sharded without a communicator: place this rank's rows only
+        const size_t slab_px = (size_t)slab_rows_for(height) * width;
+        if (St.gathered.count != slab_px * St.nranks) {
+            St.gathered.resize(slab_px * St.nranks);
+            CU(cudaMemsetAsync(St.gathered.ptr, 0, slab_px * St.nranks * sizeof(float4), St.stream));
+        }
+        CU(cudaMemcpyAsync(St.gathered.ptr + slab_px * St.rank, St.slab.ptr, slab_px * sizeof(float4),
+                           cudaMemcpyDeviceToDevice, St.stream));
+        clpt_launch_deinterleave(St.gathered.ptr, St.image.ptr, width, height, St.nranks, St.tile_rows,
+                                 slab_rows_for(height), St.stream);
+        CU(cudaGetLastError());
+        St.last_launches++;
+    }
+    CU(cudaStreamSynchronize(St.stream)); // clFinish, src/CLState.c:212
+    CU(cudaEventElapsedTime(&St.last_kernel_ms, St.ev_start, St.ev_stop));
+    if (St.flags & CLPT_FLAG_COUNTERS) {
+        CU(cudaMemcpy(St.host_counters, St.counters.ptr, sizeof(St.host_counters), cudaMemcpyDeviceToHost));
+    }
+    if (St.flags & CLPT_FLAG_ACCUMULATE) St.sample_base += (unsigned)(St.spp < 1 ? 1 : St.spp);
+}
+
+cudaStream_t clpt_state_stream() { return St.stream; }
+int clpt_state_device() { return St.device; }
+
+extern "C" {
+
+void CLSelectDevice(int ordinal) {
+    if (St.inited) FATAL("CLSelectDevice must be called before CLInit");
+    St.device = ordinal;
+}
+
+void CLInit(const char *kernel_filename, const char *kernel_name) {
+    (void)kernel_filename;
+    (void)kernel_name;
+    if (St.inited) return;
+    // same bring-up order as src/CLState.c:228-234, through the CLHandler layer
+    CLPlatform platform = CLGetPlatform();
+    CLDevice device = CLGetDevice(platform);
+    CLContext context = CLCreateContext(platform, device);
+    CLBuildProgram(kernel_filename, context, device);
+    St.device = (int)(intptr_t)device - 1;
+    St.stream = (cudaStream_t)CLCreateQueue(context, device);
+    CLCreateKernel(kernel_name ? kernel_name : "render", nullptr);
+    CU(cudaGetDeviceProperties(&St.prop, St.device));
+    CU(cudaEventCreate(&St.ev_start));
+    CU(cudaEventCreate(&St.ev_stop));
+    for (auto &e : St.ev_user) CU(cudaEventCreate(&e));
+    memset(St.cam, 0, sizeof(St.cam));
+    St.inited = true;
+}
+
+void CLTerminate(void) {
+    if (!St.inited) return;
+    release_host_kd(); // delete_kd(State.kd), src/CLState.c:223
+    CU(cudaStreamSynchronize(St.stream));
+    if (St.comm) {
+        NC(g_nccl.CommDestroy(St.comm));
+        St.comm = nullptr;
+    }
+    St.nodes.release();
+    St.leaves.release();
+    St.tri.release();
+    St.norms.release();
+    St.corners.release();
+    St.objects.release();
+    St.materials.release();
+    St.tri_material.release();
+    St.image.release();
+    St.slab.release();
+    St.gathered.release();
+    St.scratch.release();
+    St.aov_prim.release();
+    St.aov_t.release();
+    St.aov_uv.release();
+    St.counters.release();
+    St.l2_flush.release();
+    CU(cudaEventDestroy(St.ev_start));
+    CU(cudaEventDestroy(St.ev_stop));
+    for (auto &e : St.ev_user) CU(cudaEventDestroy(e));
+    CU(cudaStreamDestroy(St.stream));
+    St.stream = nullptr;
+    St.have_scene = St.have_image = St.headless = false;
+    St.objcount = 0;
+    St.rank = 0;
+    St.nranks = 1;
+    St.inited = false;
+    St.device = -1;
+}
+
+void CLSetCameraMatrixPtr(const Matrix *matrix) {
+    require_init("CLSetCameraMatrix");
+    // The reference writes 64 bytes into a device buffer the kernel re-reads per
+    // thread (src/CLState.c:67-79, src/kernel.cl:443-454); here the matrix rides
+    // in the launch parameters (constant bank), so "upload" is a host copy.
+    memcpy(St.cam, matrix, sizeof(St.cam));
+}
+
+void CLSetCameraMatrix(Matrix matrix) { CLSetCameraMatrixPtr(&matrix); }
+
+void CLSetObjects(Object *vec_objects, size_t size) {
+    require_init("CLSetObjects");
+    if (size / sizeof(Object) != (size_t)St.objcount) {
+        St.objects.resize(size);
+        St.objcount = (int)(size / sizeof(Object));
+    }
+    if (size == 0) return;
+    CU(cudaMemcpyAsync(St.objects.ptr, vec_objects, size, cudaMemcpyHostToDevice, St.stream));
+    CU(cudaStreamSynchronize(St.stream));
+}
+
+void CLSetMeshes(kd *models) {
+    require_init("CLSetMeshes");
+    if (models == nullptr || list_size(models) / sizeof(kd) == 0) return; // src/CLState.c:126-129
+    kd m = models[0];                                                     // models[0] only, :130
+    release_host_kd();
+    St.host_kd = m;
+    St.owns_kd = true;
+    upload_scene(m.node_vec, list_size(m.node_vec), m.tri_indices, list_size(m.tri_indices), m.tri_vec,
+                 list_size(m.tri_vec), m.vert_vec, list_size(m.vert_vec), m.norm_vec,
+                 m.norm_vec ? list_size(m.norm_vec) : 0);
+}
+
+void CLSetMeshesRaw(const void *nodes, size_t node_bytes, const int *tri_indices, size_t tri_index_bytes,
+                    const void *tris, size_t tri_bytes, const void *verts, size_t vert_bytes,
+                    const void *norms, size_t norm_bytes) {
+    require_init("CLSetMeshesRaw");
+    release_host_kd();
+    upload_scene((const kdnode *)nodes, node_bytes, tri_indices, tri_index_bytes, (const cl_int3 *)tris,
+                 tri_bytes, (const Vector4 *)verts, vert_bytes, (const Vector4 *)norms, norm_bytes);
+}
+
+void CLSetMaterials(const CLMaterial *materials, size_t material_bytes, const int *tri_material,
+                    size_t tri_material_bytes) {
+    require_init("CLSetMaterials");
+    static_assert(sizeof(CLMaterial) == sizeof(ClptMaterial), "material layout");
+    St.materials.upload(reinterpret_cast<const ClptMaterial *>(materials), material_bytes / sizeof(CLMaterial),
+                        St.stream);
+    const size_t n = tri_material ? tri_material_bytes / sizeof(int) : 0;
+    if (n && St.have_scene && n != (size_t)St.scene.n_prims) {
+        fprintf(stderr, "CLSetMaterials: %zu per-triangle ids for %d triangles\n", n, St.scene.n_prims);
+        exit(EXIT_FAILURE);
+    }
+    if (n) {
+        St.tri_material.upload(tri_material, n, St.stream);
+    } else {
+        St.tri_material.release();
+    }
+    rebuild_scene_struct();
+}
+
+void CLSetRenderParams(int mode, int depth, int spp, unsigned int seed, int flags) {
+    require_init("CLSetRenderParams");
+    if (mode < 0 || mode > 2) FATAL("CLSetRenderParams: mode must be 0, 1 or 2");
+    if (spp < 1) FATAL("CLSetRenderParams: spp must be >= 1");
+    St.mode = mode;
+    St.depth = depth;
+    St.spp = spp;
+    St.seed = seed;
+    St.flags = flags;
+}
+
+void CLSetMaxLeafVisits(int cap) {
+    if (cap < 1) FATAL("CLSetMaxLeafVisits: cap must be >= 1");
+    St.max_leaf_visits = cap;
+}
+
+void CLDeleteImage(void) {
+    require_init("CLDeleteImage");
+    if (!St.have_image) FATAL("CLDeleteImage: no render target"); // clReleaseMemObject(0) errors too
+    St.image.release();
+    St.slab.release();
+    St.gathered.release();
+    St.scratch.release();
+    St.aov_prim.release();
+    St.aov_t.release();
+    St.aov_uv.release();
+    St.have_image = St.headless = false;
+    St.width = St.height = 0;
+}
+
+void CLCreateImageHeadless(int width, int height) {
+    require_init("CLCreateImageHeadless");
+    if (width < 1 || height < 1) FATAL("CLCreateImageHeadless: bad size");
+    St.width = width;
+    St.height = height;
+    St.headless = true;
+    St.have_image = true;
+    alloc_targets();
+}
+
+void CLCreateImage(unsigned int texture) {
+    require_init("CLCreateImage");
+#ifdef CLPT_WITH_GL
+    clpt_gl_register(texture); // csrc/cuda/gl_interop.cu
+#else
+    (void)texture;
+    FATAL("CLCreateImage(GLuint): this build has no OpenGL interop (rebuild with -DCLPT_WITH_GL); "
+          "use CLCreateImageHeadless");
+#endif
+}
+
+void CLResetAccumulation(void) {
+    require_init("CLResetAccumulation");
+    if (!St.have_image) return;
+    clpt_launch_fill(St.image.ptr, St.image.count, 0.0f, St.stream);
+    if (St.slab.ptr) clpt_launch_fill(St.slab.ptr, St.slab.count, 0.0f, St.stream);
+    CU(cudaStreamSynchronize(St.stream));
+    St.sample_base = 0;
+}
+
+void CLExecute(int width, int height) { clpt_state_launch_frame(width, height); }
+
+void CLReadImage(float *dst_rgba, size_t bytes) {
+    require_init("CLReadImage");
+    if (!St.have_image) FATAL("CLReadImage: no render target");
+    const size_t px = (size_t)St.width * St.height;
+    if (bytes != px * sizeof(float4)) {
+        fprintf(stderr, "CLReadImage: %zu bytes given, the %dx%d float4 frame is %zu\n", bytes, St.width,
+                St.height, px * sizeof(float4));
+        exit(EXIT_FAILURE);
+    }
+    const float4 *src = St.image.ptr;
+    if (St.flags & CLPT_FLAG_ACCUMULATE) {
+        if (St.scratch.count != px) St.scratch.resize(px);
+        clpt_launch_normalise(St.image.ptr, St.scratch.ptr, px, St.stream);
+        CU(cudaGetLastError());
+        src = St.scratch.ptr;
+    }
+    CU(cudaMemcpyAsync(dst_rgba, src, bytes, cudaMemcpyDeviceToHost, St.stream));
+    CU(cudaStreamSynchronize(St.stream));
+}
+
+void CLEnableAOV(int enable) {
+    require_init("CLEnableAOV");
+    St.aov = enable != 0;
+    if (St.have_image) {
+        const size_t px = (size_t)St.width * St.height;
+        if (St.aov && St.aov_prim.count != px) {
+            St.aov_prim.resize(px);
+            St.aov_t.resize(px);
+            St.aov_uv.resize(px);
+            CU(cudaMemset(St.aov_prim.ptr, 0xff, px * sizeof(int)));
+            CU(cudaMemset(St.aov_t.ptr, 0, px * sizeof(float)));
+            CU(cudaMemset(St.aov_uv.ptr, 0, px * sizeof(float2)));
+        }
+    }
+}
+
+void CLReadAOV(int *prim_id, float *t_hit, float *uv) {
+    require_init("CLReadAOV");
+    if (!St.aov || !St.aov_prim.ptr) FATAL("CLReadAOV: AOVs are not enabled (CLEnableAOV before the frame)");
+    const size_t px = (size_t)St.width * St.height;
+    if (prim_id) CU(cudaMemcpy(prim_id, St.aov_prim.ptr, px * sizeof(int), cudaMemcpyDeviceToHost));
+    if (t_hit) CU(cudaMemcpy(t_hit, St.aov_t.ptr, px * sizeof(float), cudaMemcpyDeviceToHost));
+    if (uv) CU(cudaMemcpy(uv, St.aov_uv.ptr, px * sizeof(float2), cudaMemcpyDeviceToHost));
+}
+
+void CLGetCounters(unsigned long long out[6]) { memcpy(out, St.host_counters, sizeof(St.host_counters)); }
+float CLLastKernelMs(void) { return St.last_kernel_ms; }
+int CLLastLaunchCount(void) { return St.last_launches; }
+
+void CLEventRecord(int slot) {
+    require_init("CLEventRecord");
+    if (slot < 0 || slot >= 8) FATAL("CLEventRecord: slot out of range");
+    CU(cudaEventRecord(St.ev_user[slot], St.stream));
+}
+
+float CLEventElapsedMs(int start_slot, int stop_slot) {
+    require_init("CLEventElapsedMs");
+    if (start_slot < 0 || start_slot >= 8 || stop_slot < 0 || stop_slot >= 8)
+        FATAL("CLEventElapsedMs: slot out of range");
+    float ms = 0;
+    CU(cudaEventSynchronize(St.ev_user[stop_slot]));
+    CU(cudaEventElapsedTime(&ms, St.ev_user[start_slot], St.ev_user[stop_slot]));
+    return ms;
+}
+
+void CLFlushL2(void) {
+    require_init("CLFlushL2");
+    const size_t bytes = (size_t)St.prop.l2CacheSize * 2 > (256u << 20) ? (size_t)St.prop.l2CacheSize * 2
+                                                                         : (size_t)(256u << 20);
+    if (St.l2_flush.count != bytes) St.l2_flush.resize(bytes);
+    CU(cudaMemsetAsync(St.l2_flush.ptr, 0, bytes, St.stream));
+    CU(cudaStreamSynchronize(St.stream));
+}
+
+void CLSetTileShard(int rank, int nranks, int tile_rows) {
+    require_init("CLSetTileShard");
+    if (nranks < 1 || rank < 0 || rank >= nranks || tile_rows < 4 || (tile_rows % 4) != 0)
+        FATAL("CLSetTileShard: need 0 <= rank < nranks and tile_rows a positive multiple of 4");
+    St.rank = rank;
+    St.nranks = nranks;
+    St.tile_rows = tile_rows;
+    if (St.have_image) alloc_targets();
+}
+
+void CLDistGetUniqueId(void *id128) {
+    nccl_load();
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NC(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, sizeof(id));
+}
+
+void CLDistInit(int rank, int nranks, const void *id128, int tile_rows) {
+    require_init("CLDistInit");
+    nccl_load();
+    CLSetTileShard(rank, nranks, tile_rows);
+    if (St.comm) {
+        NC(g_nccl.CommDestroy(St.comm));
+        St.comm = nullptr;
+    }
+    if (nranks > 1) {
+        ncclUniqueId id;
+        memcpy(&id, id128, sizeof(id));
+        CU(cudaSetDevice(St.device));
+        NC(g_nccl.CommInitRank(&St.comm, nranks, id, rank));
+    }
+    if (St.have_image) alloc_targets();
+}
+
+void CLDistShutdown(void) {
+    if (St.comm) {
+        CU(cudaStreamSynchronize(St.stream));
+        NC(g_nccl.CommDestroy(St.comm));
+        St.comm = nullptr;
+    }
+    St.rank = 0;
+    St.nranks = 1;
+    if (St.inited && St.have_image) alloc_targets();
+}
+
+const char *CLDeviceName(void) {
+    require_init("CLDeviceName");
+    return St.prop.name;
+}
+
+int CLDeviceSMCount(void) {
+    require_init("CLDeviceSMCount");
+    return St.prop.multiProcessorCount;
+}
+
+} // extern "C"

@@ -1,0 +1,465 @@
+// render_kernel.cu -- the render hot path for sm_100a.
+//
+// One launch = one frame (or one rank's row tiles of it): per pixel sample,
+// camera ray generation -> stackless kd-tree traversal with ropes ->
+// Moller-Trumbore over the leaf's contiguous triangle run -> shading ->
+// in-register accumulation over the samples -> one float4 store.
+//
+// What it computes is what the reference kernel computes (src/kernel.cl:296-473,
+// see oracle/oracle_kernel.c for the restatement it is checked against); how
+// it computes it is not: the camera matrix comes from the constant bank
+// instead of global memory, split nodes are 8 bytes and siblings adjacent,
+// leaves are one aligned 64-byte record, triangles are pre-gathered per leaf
+// with the edge vectors precomputed, the hit normal is evaluated once per ray
+// instead of once per accepted candidate, the tail recursion is a loop, and
+// warps cover 8x4 pixel tiles.
+//
+// Numerics: every fp32 operation that decides a hit is written with the
+// round-to-nearest intrinsics (__fmul_rn, __fadd_rn, ...), which the compiler
+// never contracts into FMAs, and in the reference's operand order, so hit
+// ids, t, u, v and colours are bit-identical to the restatement compiled with
+// -ffp-contract=off.  Division and square root are the IEEE-rounded ones.
+#include "clpt_device.cuh"
+
+namespace {
+
+struct V3 {
+    float x, y, z;
+};
+
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ V3 mk(float x, float y, float z) { V3 r = { x, y, z }; return r; }
+__device__ __forceinline__ V3 vadd(V3 a, V3 b) { return mk(fadd(a.x, b.x), fadd(a.y, b.y), fadd(a.z, b.z)); }
+__device__ __forceinline__ V3 vsub(V3 a, V3 b) { return mk(fsub(a.x, b.x), fsub(a.y, b.y), fsub(a.z, b.z)); }
+__device__ __forceinline__ V3 vscale(V3 a, float k) { return mk(fmul(a.x, k), fmul(a.y, k), fmul(a.z, k)); }
+__device__ __forceinline__ float vdot(V3 a, V3 b) {
+    return fadd(fadd(fmul(a.x, b.x), fmul(a.y, b.y)), fmul(a.z, b.z));
+}
+__device__ __forceinline__ V3 vcross(V3 a, V3 b) {
+    return mk(fsub(fmul(a.y, b.z), fmul(a.z, b.y)), fsub(fmul(a.z, b.x), fmul(a.x, b.z)),
+              fsub(fmul(a.x, b.y), fmul(a.y, b.x)));
+}
+__device__ __forceinline__ V3 vnormalize(V3 a) {
+    float len = __fsqrt_rn(vdot(a, a));
+    return mk(fdiv(a.x, len), fdiv(a.y, len), fdiv(a.z, len));
+}
+__device__ __forceinline__ V3 xyz(float4 a) { return mk(a.x, a.y, a.z); }
+
+struct Hit {
+    int did_hit;
+    int prim;
+    int ref; // triangle slot of the accepted hit
+    float t, u, v;
+};
+
+struct Counters {
+    unsigned int rays, splits, leaves, tris, shade_vn, capped;
+};
+
+// Traversal of one ray: src/kernel.cl:311-389.
+template <bool COUNT>
+__device__ __forceinline__ Hit closest_hit(const ClptScene &S, V3 o, V3 d, int max_visits,
+                                           Counters &cn) {
+    Hit h;
+    h.did_hit = 0;
+    h.prim = -1;
+    h.ref = 0;
+    h.t = 0.0f;
+    h.u = 0.0f;
+    h.v = 0.0f;
+    if (COUNT) cn.rays++;
+
+    const V3 inv = mk(fdiv(1.0f, d.x), fdiv(1.0f, d.y), fdiv(1.0f, d.z));
+    const bool sx = inv.x < 0.0f, sy = inv.y < 0.0f, sz = inv.z < 0.0f;
+
+    float tmin, tmax;
+    { // root clip, kernel.cl:101-144
+        const float nx = sx ? S.root_max[0] : S.root_min[0], fx = sx ? S.root_min[0] : S.root_max[0];
+        const float ny = sy ? S.root_max[1] : S.root_min[1], fy = sy ? S.root_min[1] : S.root_max[1];
+        const float nz = sz ? S.root_max[2] : S.root_min[2], fz = sz ? S.root_min[2] : S.root_max[2];
+        tmin = fmul(fsub(nx, o.x), inv.x);
+        tmax = fmul(fsub(fx, o.x), inv.x);
+        const float tymin = fmul(fsub(ny, o.y), inv.y), tymax = fmul(fsub(fy, o.y), inv.y);
+        if ((tmin > tymax) || (tymin > tmax)) return h;
+        if (tymin > tmin) tmin = tymin;
+        if (tymax < tmax) tmax = tymax;
+        const float tzmin = fmul(fsub(nz, o.z), inv.z), tzmax = fmul(fsub(fz, o.z), inv.z);
+        if ((tmin > tzmax) || (tzmin > tmax)) return h;
+        if (tzmin > tmin) tmin = tzmin;
+        if (tzmax < tmax) tmax = tzmax;
+        if (!(tmax > 0.0f)) return h;
+    }
+    V3 p1 = o;
+    if (tmin > 0.0f) p1 = vadd(p1, vscale(d, tmin));
+
+    int index = 0;
+    int visits = 0;
+    float min_hit = 0.0f;
+    const uint2 *__restrict__ nodes = S.nodes;
+    const float4 *__restrict__ leaves = S.leaves;
+    const float4 *__restrict__ tri = S.tri;
+
+    for (;;) {
+        // descend to the leaf containing p1, kernel.cl:325-330
+        uint2 n = __ldg(&nodes[index]);
+        while ((n.y & 3u) != 3u) {
+            const unsigned axis = n.y & 3u;
+            const float p = axis == 0 ? p1.x : (axis == 1 ? p1.y : p1.z);
+            index = (int)(n.y >> 2) + (p > __uint_as_float(n.x) ? 1 : 0);
+            n = __ldg(&nodes[index]);
+            if (COUNT) cn.splits++;
+        }
+        if (COUNT) cn.leaves++;
+        const float4 *L = leaves + 4 * (size_t)n.x;
+        const float4 lmin = __ldg(L), lmax = __ldg(L + 1);
+        const int first = __float_as_int(lmin.w), count = __float_as_int(lmax.w);
+
+        // triangle run of the leaf, kernel.cl:333-368 / 227-255
+        for (int i = first; i < first + count; i++) {
+            const float4 a = __ldg(tri + 3 * (size_t)i);
+            const float4 b = __ldg(tri + 3 * (size_t)i + 1);
+            const float4 c = __ldg(tri + 3 * (size_t)i + 2);
+            if (COUNT) cn.tris++;
+            const V3 e1 = xyz(b), e2 = xyz(c);
+            const V3 pvec = vcross(d, e2);
+            const float det = vdot(e1, pvec);
+            if (det < 0.0f) continue;
+            const float idet = fdiv(1.0f, det);
+            const V3 tvec = vsub(o, xyz(a));
+            const float u = fmul(vdot(tvec, pvec), idet);
+            if (u < 0.0f || u > 1.0f) continue;
+            const V3 qvec = vcross(tvec, e1);
+            const float v = fmul(vdot(d, qvec), idet);
+            if (v < 0.0f || fadd(u, v) > 1.0f) continue;
+            const float t = fmul(vdot(e2, qvec), idet);
+            if (!(t > 0.0f)) continue;
+            if (!h.did_hit || t <= min_hit) { // the later triangle wins ties (:344)
+                h.did_hit = 1;
+                min_hit = t;
+                h.prim = __float_as_int(a.w);
+                h.ref = i;
+                h.u = u;
+                h.v = v;
+            }
+        }
+
+        // leaf slab interval and exit face, kernel.cl:146-174
+        int far = sx ? 0 : 1;
+        {
+            const float nx = sx ? lmax.x : lmin.x, fx = sx ? lmin.x : lmax.x;
+            const float ny = sy ? lmax.y : lmin.y, fy = sy ? lmin.y : lmax.y;
+            const float nz = sz ? lmax.z : lmin.z, fz = sz ? lmin.z : lmax.z;
+            tmin = fmul(fsub(nx, o.x), inv.x);
+            tmax = fmul(fsub(fx, o.x), inv.x);
+            const float tymin = fmul(fsub(ny, o.y), inv.y), tymax = fmul(fsub(fy, o.y), inv.y);
+            if (tymin > tmin) tmin = tymin;
+            if (tymax < tmax) {
+                tmax = tymax;
+                far = sy ? 2 : 3;
+            }
+            const float tzmin = fmul(fsub(nz, o.z), inv.z), tzmax = fmul(fsub(fz, o.z), inv.z);
+            if (tzmin > tmin) tmin = tzmin;
+            if (tzmax < tmax) {
+                tmax = tzmax;
+                far = sz ? 4 : 5;
+            }
+        }
+        // 0.001 is a double literal in the reference (:381)
+        if (h.did_hit && (double)tmin + 0.001 > (double)min_hit) break;
+        index = __ldg(reinterpret_cast<const int *>(L + 2) + far);
+        p1 = vadd(o, vscale(d, tmax));
+        if (index == -1) break;
+        if (++visits >= max_visits) {
+            if (COUNT) cn.capped++;
+            break;
+        }
+    }
+    h.t = min_hit;
+    return h;
+}
+
+// Shading normal of an accepted hit, kernel.cl:349-365.
+template <bool COUNT>
+__device__ __forceinline__ V3 hit_normal(const ClptScene &S, const Hit &h, Counters &cn) {
+    const int4 c1 = __ldg(S.corners + 3 * (size_t)h.prim);
+    if (c1.y >= 0) {
+        const int4 c2 = __ldg(S.corners + 3 * (size_t)h.prim + 1);
+        const int4 c3 = __ldg(S.corners + 3 * (size_t)h.prim + 2);
+        const V3 n1 = xyz(__ldg(S.norms + c1.y)), n2 = xyz(__ldg(S.norms + c2.y)),
+                 n3 = xyz(__ldg(S.norms + c3.y));
+        const float w = fsub(fsub(1.0f, h.u), h.v);
+        if (COUNT) cn.shade_vn++;
+        return vnormalize(vadd(vadd(vscale(n1, w), vscale(n2, h.u)), vscale(n3, h.v)));
+    }
+    const V3 e1 = xyz(__ldg(S.tri + 3 * (size_t)h.ref + 1));
+    const V3 e2 = xyz(__ldg(S.tri + 3 * (size_t)h.ref + 2));
+    return vnormalize(vcross(e1, e2));
+}
+
+// Philox4x32-10, counter (pixel, sample, dimension block, lane), key (seed, 'clpt').
+__device__ __forceinline__ void philox(unsigned c[4], unsigned k0, unsigned k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const unsigned n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0;
+        c[1] = lo1;
+        c[2] = n2;
+        c[3] = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+__device__ __forceinline__ float u01(unsigned x) { return fmul((float)(x >> 8), 0x1p-24f); }
+#define CLPT_KEY1 0x636c7074u
+
+// Cosine-weighted direction about n (extension; oracle_kernel.c cosine_dir).
+__device__ __forceinline__ V3 cosine_dir(V3 n, unsigned pixel, unsigned sample, unsigned bounce,
+                                         unsigned seed) {
+    float a = 0.0f, b = 0.0f;
+    bool found = false;
+#pragma unroll 1
+    for (unsigned blk = 0; blk < 2 && !found; blk++) {
+        unsigned c[4] = { pixel, sample, 1u + bounce, blk };
+        philox(c, seed, CLPT_KEY1);
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const float x = fsub(fmul(2.0f, u01(c[2 * k])), 1.0f);
+            const float y = fsub(fmul(2.0f, u01(c[2 * k + 1])), 1.0f);
+            if (!found && fadd(fmul(x, x), fmul(y, y)) <= 1.0f) {
+                a = x;
+                b = y;
+                found = true;
+            }
+        }
+    }
+    const float zz = fsub(fsub(1.0f, fmul(a, a)), fmul(b, b));
+    const float z = __fsqrt_rn(zz > 0.0f ? zz : 0.0f);
+    const float sg = n.z >= 0.0f ? 1.0f : -1.0f;
+    const float p = fdiv(-1.0f, fadd(sg, n.z));
+    const float q = fmul(fmul(n.x, n.y), p);
+    const V3 t1 = mk(fadd(1.0f, fmul(fmul(fmul(sg, n.x), n.x), p)), fmul(sg, q), fmul(-sg, n.x));
+    const V3 t2 = mk(q, fadd(sg, fmul(fmul(n.y, n.y), p)), -n.y);
+    return vnormalize(vadd(vadd(vscale(t1, a), vscale(t2, b)), vscale(n, z)));
+}
+
+__device__ __forceinline__ V3 unproject(const float *M, V3 X) { // kernel.cl:89-94
+    const float w = fadd(fadd(fadd(fmul(M[12], X.x), fmul(M[13], X.y)), fmul(M[14], X.z)), M[15]);
+    const float a = fadd(fadd(fadd(fmul(M[0], X.x), fmul(M[1], X.y)), fmul(M[2], X.z)), M[3]);
+    const float b = fadd(fadd(fadd(fmul(M[4], X.x), fmul(M[5], X.y)), fmul(M[6], X.z)), M[7]);
+    const float c = fadd(fadd(fadd(fmul(M[8], X.x), fmul(M[9], X.y)), fmul(M[10], X.z)), M[11]);
+    return mk(fdiv(a, w), fdiv(b, w), fdiv(c, w));
+}
+
+// 256 threads = 8 warps; a warp is an 8x4 pixel tile, a block 32x8 pixels.
+constexpr int BLOCK_W = 32, BLOCK_H = 8;
+
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(256)
+render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptFrame F) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * BLOCK_W + (warp & 3) * 8 + (lane & 7);
+    const int ly = blockIdx.y * BLOCK_H + (warp >> 2) * 4 + (lane >> 3); // row within this rank's slab
+    // slab row -> image row: tiles of tile_rows rows dealt round-robin to ranks
+    const int lt = ly / F.tile_rows;
+    const int y = (lt * F.nranks + F.rank) * F.tile_rows + (ly - lt * F.tile_rows);
+    Counters cn = { 0, 0, 0, 0, 0, 0 };
+    if (x < F.width && y < F.height && ly < F.local_rows) {
+        const float *M = F.cam;
+        const unsigned pixel = (unsigned)(y * F.width + x);
+        const V3 origin = mk(fdiv(M[2], M[14]), fdiv(M[6], M[14]), fdiv(M[10], M[14])); // :443-445
+        V3 acc = mk(0.0f, 0.0f, 0.0f);
+        const int spp = F.spp < 1 ? 1 : F.spp;
+        for (int s = 0; s < spp; s++) {
+            const unsigned sample = F.sample_base + (unsigned)s;
+            float fx = fsub((float)(unsigned)x, fdiv((float)(unsigned)F.width, 2.0f));
+            float fy = fsub((float)(unsigned)y, fdiv((float)(unsigned)F.height, 2.0f));
+            if (F.flags & CLPT_F_JITTER) {
+                unsigned c[4] = { pixel, sample, 0u, 0u };
+                philox(c, F.seed, CLPT_KEY1);
+                fx = fadd(fx, fsub(u01(c[0]), 0.5f));
+                fy = fadd(fy, fsub(u01(c[1]), 0.5f));
+            }
+            const V3 ncp = unproject(M, mk(fx, fy, -1.0f));
+            const V3 fcp = unproject(M, mk(fx, fy, 1.0f));
+            V3 o = origin;
+            V3 d = vnormalize(vsub(fcp, ncp));
+            V3 colour;
+            if (MODE == 2) {
+                V3 Lsum = mk(0.0f, 0.0f, 0.0f), T = mk(1.0f, 1.0f, 1.0f);
+                for (int seg = 0; seg < F.depth; seg++) {
+                    const Hit h = closest_hit<COUNT>(S, o, d, F.max_leaf_visits, cn);
+                    if (seg == 0 && s == 0 && F.aov_prim) {
+                        const size_t px = (size_t)y * F.width + x;
+                        F.aov_prim[px] = h.did_hit ? h.prim : -1;
+                        F.aov_t[px] = h.did_hit ? h.t : 0.0f;
+                        F.aov_uv[px] = make_float2(h.u, h.v);
+                    }
+                    if (!h.did_hit) {
+                        Lsum = vadd(Lsum, T);
+                        break;
+                    }
+                    const V3 nrm = hit_normal<COUNT>(S, h, cn);
+                    float al[3] = { 0.5f, 0.5f, 0.5f }, em[3] = { 0.0f, 0.0f, 0.0f };
+                    int kind = 0;
+                    if (S.n_materials > 0) {
+                        int m = S.tri_material ? __ldg(S.tri_material + h.prim) : 0;
+                        if (m < 0 || m >= S.n_materials) m = 0;
+                        const ClptMaterial *mp = S.materials + m;
+                        al[0] = mp->albedo[0]; al[1] = mp->albedo[1]; al[2] = mp->albedo[2];
+                        em[0] = mp->emission[0]; em[1] = mp->emission[1]; em[2] = mp->emission[2];
+                        kind = mp->kind;
+                    }
+                    Lsum = vadd(Lsum, mk(fmul(T.x, em[0]), fmul(T.y, em[1]), fmul(T.z, em[2])));
+                    T = mk(fmul(T.x, al[0]), fmul(T.y, al[1]), fmul(T.z, al[2]));
+                    V3 hp = vadd(o, vscale(d, h.t));
+                    V3 nd;
+                    if (kind == 1) {
+                        nd = vnormalize(vsub(d, vscale(nrm, fmul(2.0f, vdot(d, nrm)))));
+                    } else {
+                        nd = cosine_dir(nrm, pixel, sample, (unsigned)seg, F.seed);
+                    }
+                    o = vadd(hp, vscale(nd, 0.0001f));
+                    d = nd;
+                }
+                colour = Lsum;
+            } else {
+                // modes A/B: kernel.cl:296-422 with the tail recursion as a loop
+                V3 col = mk(0.0f, 0.0f, 0.0f);
+                float str = 1.0f;
+                bool done = false;
+                int depth = F.depth;
+                if (MODE == 0) depth = depth > 0 ? 1 : 0;
+                colour = col;
+                for (; depth > 0; depth--) {
+                    const Hit h = closest_hit<COUNT>(S, o, d, F.max_leaf_visits, cn);
+                    if (depth == (MODE == 0 ? 1 : F.depth) && s == 0 && F.aov_prim) {
+                        const size_t px = (size_t)y * F.width + x;
+                        F.aov_prim[px] = h.did_hit ? h.prim : -1;
+                        F.aov_t[px] = h.did_hit ? h.t : 0.0f;
+                        F.aov_uv[px] = make_float2(h.u, h.v);
+                    }
+                    if (!h.did_hit) break;
+                    const V3 nrm = hit_normal<COUNT>(S, h, cn);
+                    const V3 nc = mk(fdiv(fadd(nrm.x, 1.0f), 2.0f), fdiv(fadd(nrm.y, 1.0f), 2.0f),
+                                     fdiv(fadd(nrm.z, 1.0f), 2.0f));
+                    if (MODE == 0) { // the `return` at :396
+                        colour = nc;
+                        done = true;
+                        break;
+                    }
+                    V3 no = vadd(o, vscale(d, h.t));
+                    const V3 nd = vnormalize(vsub(d, vscale(nrm, fmul(2.0f, vdot(d, nrm)))));
+                    no = vadd(no, vscale(nd, 0.0001f));
+                    col = vadd(vscale(col, fsub(1.0f, str)), vscale(nc, str));
+                    str = fmul(str, 0.2f);
+                    o = no;
+                    d = nd;
+                }
+                if (!done) { // :421
+                    const float k = fsub(1.0f, str);
+                    colour = mk(fadd(fmul(k, col.x), str), fadd(fmul(k, col.y), str),
+                                fadd(fmul(k, col.z), str));
+                }
+            }
+            acc = vadd(acc, colour);
+        }
+        float4 *dst = F.target + (size_t)ly * F.width + x;
+        if (F.flags & CLPT_F_ACCUMULATE) {
+            float4 prev = *dst;
+            *dst = make_float4(fadd(prev.x, acc.x), fadd(prev.y, acc.y), fadd(prev.z, acc.z),
+                               fadd(prev.w, (float)spp));
+        } else if (spp == 1) {
+            *dst = make_float4(acc.x, acc.y, acc.z, 1.0f);
+        } else {
+            const float k = fdiv(1.0f, (float)spp);
+            *dst = make_float4(fmul(acc.x, k), fmul(acc.y, k), fmul(acc.z, k), 1.0f);
+        }
+    }
+    if (COUNT) {
+        unsigned v[6] = { cn.rays, cn.splits, cn.leaves, cn.tris, cn.shade_vn, cn.capped };
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            unsigned s = v[k];
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+            if (lane == 0 && s) atomicAdd(F.counters + k, (unsigned long long)s);
+        }
+    }
+}
+
+// Gathered slabs [rank][slab_rows][width] -> image rows.
+__global__ void deinterleave_kernel(const float4 *__restrict__ gathered, float4 *__restrict__ image,
+                                    int width, int height, int nranks, int tile_rows,
+                                    int slab_rows) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)width * height) return;
+    const int y = (int)(i / width), x = (int)(i - (size_t)y * width);
+    const int t = y / tile_rows, r = t % nranks, lt = t / nranks;
+    const int ly = lt * tile_rows + (y - t * tile_rows);
+    image[i] = gathered[((size_t)r * slab_rows + ly) * width + x];
+}
+
+__global__ void fill_kernel(float4 *dst, size_t n, float value) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = make_float4(value, value, value, value);
+}
+
+// Progressive target (sum, count in .w) -> displayable average.
+__global__ void normalise_kernel(const float4 *__restrict__ src, float4 *__restrict__ dst, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 s = src[i];
+    if (s.w > 0.0f) {
+        const float k = __fdiv_rn(1.0f, s.w);
+        dst[i] = make_float4(__fmul_rn(s.x, k), __fmul_rn(s.y, k), __fmul_rn(s.z, k), 1.0f);
+    } else {
+        dst[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+}
+
+template <int MODE>
+void launch_mode(const ClptScene &scene, const ClptFrame &frame, dim3 grid, cudaStream_t stream) {
+    if (frame.flags & CLPT_F_COUNTERS) {
+        render_kernel<MODE, true><<<grid, 256, 0, stream>>>(scene, frame);
+    } else {
+        render_kernel<MODE, false><<<grid, 256, 0, stream>>>(scene, frame);
+    }
+}
+
+} // namespace
+
+void clpt_launch_render(const ClptScene &scene, const ClptFrame &frame, cudaStream_t stream) {
+    dim3 grid((frame.width + BLOCK_W - 1) / BLOCK_W, (frame.local_rows + BLOCK_H - 1) / BLOCK_H);
+    if (grid.x == 0 || grid.y == 0) return;
+    switch (frame.mode) {
+    case 0: launch_mode<0>(scene, frame, grid, stream); break;
+    case 1: launch_mode<1>(scene, frame, grid, stream); break;
+    default: launch_mode<2>(scene, frame, grid, stream); break;
+    }
+}
+
+void clpt_launch_deinterleave(const float4 *gathered, float4 *image, int width, int height,
+                              int nranks, int tile_rows, int slab_rows, cudaStream_t stream) {
+    const size_t n = (size_t)width * height;
+    if (n == 0) return;
+    deinterleave_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(gathered, image, width, height,
+                                                                         nranks, tile_rows, slab_rows);
+}
+
+void clpt_launch_fill(float4 *dst, size_t n, float value, cudaStream_t stream) {
+    if (n == 0) return;
+    fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dst, n, value);
+}
+
+void clpt_launch_normalise(const float4 *src, float4 *dst, size_t n, cudaStream_t stream) {
+    if (n == 0) return;
+    normalise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, dst, n);
+}
+
+const void *clpt_render_kernel_symbol(void) {
+    return reinterpret_cast<const void *>(&render_kernel<0, false>);
+}

@@ -1,0 +1,179 @@
+// scene_pack.cpp -- wire format -> device layout (host side of CLSetMeshes).
+//
+// Input is exactly what the reference uploads verbatim (src/CLState.c:124-202):
+// the 68-byte preorder node array, tri_indices, three cl_int3 corners per
+// triangle, float4 verts.  Output is the layout documented in clpt_device.cuh.
+// The tree TOPOLOGY, the order of triangles inside each leaf and every float
+// are preserved, so a traversal of the packed scene visits the same leaves and
+// triangles in the same order as the reference kernel walking the input.
+#include "scene_pack.h"
+
+#include <cstdio>
+#include <cstring>
+
+namespace {
+
+inline int as_int(float f) {
+    int i;
+    std::memcpy(&i, &f, 4);
+    return i;
+}
+inline float as_float(int i) {
+    float f;
+    std::memcpy(&f, &i, 4);
+    return f;
+}
+inline uint32_t float_bits(float f) {
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    return u;
+}
+
+} // namespace
+
+bool clpt_pack_scene(const kdnode *nodes, size_t n_nodes, const int *tri_indices, size_t n_refs,
+                     const cl_int3 *corners, size_t n_corners, const Vector4 *verts, size_t n_verts,
+                     size_t n_norms, ClptPackedScene &out, std::string &err) {
+    char msg[256];
+    if (n_nodes == 0) {
+        err = "empty node array";
+        return false;
+    }
+    if (n_nodes >= (1u << 30)) {
+        err = "too many nodes for the 30-bit child field";
+        return false;
+    }
+    const size_t n_prims = n_corners / 3;
+
+    // ---- renumber nodes: depth-first, siblings adjacent ----
+    std::vector<int> new_of(n_nodes, -1), leaf_of(n_nodes, -1);
+    int n_leaves = 0;
+    for (size_t i = 0; i < n_nodes; i++) {
+        if (nodes[i].type == KD_LEAF) {
+            leaf_of[i] = n_leaves++; // preorder rank: neighbours in space stay neighbours in memory
+        } else if (nodes[i].type != KD_SPLIT) {
+            snprintf(msg, sizeof msg, "node %zu has type %d", i, nodes[i].type);
+            err = msg;
+            return false;
+        }
+    }
+    std::vector<int> stack;
+    stack.reserve(128);
+    int next = 1;
+    new_of[0] = 0;
+    stack.push_back(0);
+    while (!stack.empty()) {
+        const int o = stack.back();
+        stack.pop_back();
+        if (nodes[o].type != KD_SPLIT) continue;
+        const int c0 = nodes[o].split.children[0], c1 = nodes[o].split.children[1];
+        if (c0 < 0 || c1 < 0 || (size_t)c0 >= n_nodes || (size_t)c1 >= n_nodes || new_of[c0] != -1 ||
+            new_of[c1] != -1 || nodes[o].split.axis < 0 || nodes[o].split.axis > 2) {
+            snprintf(msg, sizeof msg, "split node %d is malformed (children %d,%d axis %d)", o, c0, c1,
+                     nodes[o].split.axis);
+            err = msg;
+            return false;
+        }
+        new_of[c0] = next;
+        new_of[c1] = next + 1;
+        next += 2;
+        stack.push_back(c1);
+        stack.push_back(c0);
+    }
+    const int n_packed = next;
+
+    out.nodes.assign((size_t)n_packed, ClptNode8{ 0, 0 });
+    out.leaves.assign((size_t)n_leaves * 4, ClptFloat4{ 0, 0, 0, 0 });
+    for (size_t i = 0; i < n_nodes; i++) {
+        const int ni = new_of[i];
+        if (ni < 0) continue; // unreachable from the root
+        const kdnode &k = nodes[i];
+        if (k.type == KD_SPLIT) {
+            out.nodes[ni].x = float_bits(k.split.value);
+            out.nodes[ni].y = ((uint32_t)new_of[k.split.children[0]] << 2) | (uint32_t)k.split.axis;
+        } else {
+            const int li = leaf_of[i];
+            out.nodes[ni].x = (uint32_t)li;
+            out.nodes[ni].y = 3u;
+            const int first = k.leaf.tris, count = k.leaf.tri_count;
+            if (count < 0 || (count > 0 && (first < 0 || (size_t)first + (size_t)count > n_refs))) {
+                snprintf(msg, sizeof msg, "leaf node %zu references triangles [%d,+%d) of %zu", i, first,
+                         count, n_refs);
+                err = msg;
+                return false;
+            }
+            ClptFloat4 *L = &out.leaves[(size_t)li * 4];
+            L[0] = ClptFloat4{ k.min.s[0], k.min.s[1], k.min.s[2], as_float(count > 0 ? first : 0) };
+            L[1] = ClptFloat4{ k.max.s[0], k.max.s[1], k.max.s[2], as_float(count) };
+            int ropes[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+            for (int f = 0; f < 6; f++) {
+                const int r = k.leaf.ropes[f];
+                if (r == -1) {
+                    ropes[f] = -1;
+                } else if (r < 0 || (size_t)r >= n_nodes || new_of[r] < 0) {
+                    snprintf(msg, sizeof msg, "leaf node %zu rope %d -> %d is out of range", i, f, r);
+                    err = msg;
+                    return false;
+                } else {
+                    ropes[f] = new_of[r];
+                }
+            }
+            L[2] = ClptFloat4{ as_float(ropes[0]), as_float(ropes[1]), as_float(ropes[2]), as_float(ropes[3]) };
+            L[3] = ClptFloat4{ as_float(ropes[4]), as_float(ropes[5]), 0, 0 };
+        }
+    }
+
+    // ---- pre-gather triangles in leaf order, edges precomputed ----
+    out.tri.assign(n_refs * 3, ClptFloat4{ 0, 0, 0, 0 });
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (long long s = 0; s < (long long)n_refs; s++) {
+        const int b = tri_indices[s];
+        if (b < 0 || (size_t)b >= n_prims) {
+            bad |= 1;
+            continue;
+        }
+        const int i0 = corners[3 * (size_t)b].s[0], i1 = corners[3 * (size_t)b + 1].s[0],
+                  i2 = corners[3 * (size_t)b + 2].s[0];
+        if (i0 < 0 || i1 < 0 || i2 < 0 || (size_t)i0 >= n_verts || (size_t)i1 >= n_verts ||
+            (size_t)i2 >= n_verts) {
+            bad |= 2;
+            continue;
+        }
+        const Vector4 &v0 = verts[i0], &v1 = verts[i1], &v2 = verts[i2];
+        ClptFloat4 *T = &out.tri[(size_t)s * 3];
+        T[0] = ClptFloat4{ v0.s[0], v0.s[1], v0.s[2], as_float(b) };
+        // one fp32 subtraction each, the same rounding as `v1 - v0` in the kernel
+        T[1] = ClptFloat4{ v1.s[0] - v0.s[0], v1.s[1] - v0.s[1], v1.s[2] - v0.s[2], 0 };
+        T[2] = ClptFloat4{ v2.s[0] - v0.s[0], v2.s[1] - v0.s[1], v2.s[2] - v0.s[2], 0 };
+    }
+    if (bad) {
+        err = (bad & 1) ? "tri_indices entry out of range" : "triangle corner references a missing vertex";
+        return false;
+    }
+    // vertex-normal indices are dereferenced when shading.  Like the reference
+    // (kernel.cl:349) only the FIRST corner decides whether normals are used, so
+    // when it has one the other two must be valid as well.
+    for (size_t p = 0; p < n_prims; p++) {
+        if (corners[3 * p].s[1] < 0) continue;
+        for (int c = 0; c < 3; c++) {
+            const int vn = corners[3 * p + c].s[1];
+            if (vn < 0 || (size_t)vn >= n_norms) {
+                snprintf(msg, sizeof msg, "triangle %zu corner %d references normal %d of %zu", p, c, vn,
+                         n_norms);
+                err = msg;
+                return false;
+            }
+        }
+    }
+    for (int a = 0; a < 3; a++) {
+        out.root_min[a] = nodes[0].min.s[a];
+        out.root_max[a] = nodes[0].max.s[a];
+    }
+    out.n_nodes = n_packed;
+    out.n_leaves = n_leaves;
+    out.n_refs = (int)n_refs;
+    out.n_prims = (int)n_prims;
+    (void)as_int;
+    return true;
+}

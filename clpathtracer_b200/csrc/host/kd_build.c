@@ -1,0 +1,534 @@
+/* kd_build.c -- kd-tree builder with ropes (clpt_host.h "kd-tree").
+ *
+ * Produces the reference's wire format: a PREORDER array of 68-byte nodes
+ * (left child is always parent+1), a tri_indices array filled leaf by leaf in
+ * preorder, and six neighbour links ("ropes") per leaf.  At depth 15 / 25 bins
+ * the output is byte-identical to the reference builder
+ * (src/kd_tree.c:95-276); tests/test_host_parity.py pins that against the
+ * reference's own unmodified code.
+ *
+ * The split rule is the reference's, restated (src/kd_tree.c:113-157):
+ *   for axis in x,y,z (skipped when the extent < 1e-9, compared in double)
+ *     for i in 0..nbins-1:  d = (i+1)/(nbins+1),  v = min[axis] + d*extent
+ *        SL = half-box area on the low side  + sum of areas of triangles with
+ *             a vertex <= v;  SR likewise on the high side (vertex >= v)
+ *        cost = NL*SL + NR*SR          (fp32, triangles summed in list order)
+ *   keep the FIRST candidate that attains the minimum cost.
+ *   Stop (leaf) at <= 1 triangle, depth 0, no candidate, or a plane on the
+ *   cell boundary.  Triangles with a vertex within 1e-9 (double) of the plane
+ *   go to both children.
+ *
+ * What is different from the reference is how that rule is evaluated: here
+ * triangles live in per-node structure-of-arrays (per-axis min/max + area,
+ * 32 B per reference instead of an 80 B struct copy), the candidate planes of
+ * large nodes are evaluated concurrently (each candidate still sums its
+ * triangles in list order, so every fp32 cost is bit-identical to a serial
+ * evaluation), subtrees are built as OpenMP tasks into a linked tree, and the
+ * preorder arrays are emitted in one pass at the end.  Depth and bin count
+ * are run-time parameters.
+ */
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "clpt_host.h"
+
+#define KD_EPS 0.000000001 /* double, like src/kd_tree.c:10 */
+
+/* Triangle references of one cell, structure-of-arrays. */
+typedef struct tri_set {
+    int n;
+    int *id;      /* original triangle index */
+    float *lo[3]; /* per-axis min over the three vertices */
+    float *hi[3]; /* per-axis max over the three vertices */
+    float *area;  /* |cross|/2 */
+    void *block;
+} tri_set;
+
+typedef struct bnode {
+    float bmin[3], bmax[3];
+    int leaf;
+    float value;
+    int axis;
+    struct bnode *kid[2];
+    int *ids; /* leaf: triangle ids in list order */
+    int nids;
+} bnode;
+
+static void *
+xmalloc(size_t n) {
+    void *p = malloc(n ? n : 1);
+    if (p == NULL) {
+        perror("malloc");
+        exit(EXIT_FAILURE);
+    }
+    return p;
+}
+
+static tri_set
+tri_set_alloc(int n) {
+    tri_set s;
+    size_t cap = (size_t)(n > 0 ? n : 1);
+    s.block = xmalloc(cap * 8 * sizeof(float));
+    float *f = s.block;
+    s.n = 0;
+    s.id = (int *)f;
+    for (int a = 0; a < 3; a++) {
+        s.lo[a] = f + cap * (1 + a);
+        s.hi[a] = f + cap * (4 + a);
+    }
+    s.area = f + cap * 7;
+    return s;
+}
+
+static void
+tri_set_free(tri_set *s) {
+    free(s->block);
+    s->block = NULL;
+}
+
+static inline void
+tri_set_push(tri_set *dst, const tri_set *src, int t) {
+    int k = dst->n++;
+    dst->id[k] = src->id[t];
+    for (int a = 0; a < 3; a++) {
+        dst->lo[a][k] = src->lo[a][t];
+        dst->hi[a][k] = src->hi[a][t];
+    }
+    dst->area[k] = src->area[t];
+}
+
+static bnode *
+make_leaf(const float *bmin, const float *bmax, const tri_set *s) {
+    bnode *b = xmalloc(sizeof(*b));
+    memcpy(b->bmin, bmin, sizeof(b->bmin));
+    memcpy(b->bmax, bmax, sizeof(b->bmax));
+    b->leaf = 1;
+    b->kid[0] = b->kid[1] = NULL;
+    b->nids = s->n;
+    b->ids = xmalloc(sizeof(int) * (size_t)s->n);
+    memcpy(b->ids, s->id, sizeof(int) * (size_t)s->n);
+    return b;
+}
+
+/* Cost of one candidate plane.  Sums run over the triangles in list order in
+ * fp32 (src/kd_tree.c:126-145).  `bound` is a cost already achieved by another
+ * candidate: once the partial cost exceeds it the candidate cannot win (all
+ * terms are non-negative, so the cost only grows) and +inf is returned. */
+static float
+plane_cost(const tri_set *s, int axis, float v, float SL, float SR,
+           const volatile float *bound) {
+    const float *lo = s->lo[axis], *hi = s->hi[axis], *area = s->area;
+    int NL = 0, NR = 0;
+    int n = s->n;
+    for (int base = 0; base < n; base += 512) {
+        int end = base + 512 < n ? base + 512 : n;
+        for (int t = base; t < end; t++) {
+            int l = lo[t] <= v, r = hi[t] >= v;
+            NL += l;
+            NR += r;
+            SL += l ? area[t] : 0.0f; /* x + 0 == x: same bits as a skipped add */
+            SR += r ? area[t] : 0.0f;
+        }
+        if (bound && NL * SL + NR * SR > *bound) {
+            return INFINITY;
+        }
+    }
+    return NL * SL + NR * SR;
+}
+
+typedef struct candidate {
+    int axis;
+    float v, SL0, SR0, cost;
+} candidate;
+
+static bnode *
+build_cell(tri_set s, const float *bmin, const float *bmax, int depth,
+           int nbins) {
+    bnode *out;
+    if (s.n <= 1 || depth == 0) {
+        out = make_leaf(bmin, bmax, &s);
+        tri_set_free(&s);
+        return out;
+    }
+    float ext[3];
+    for (int a = 0; a < 3; a++) {
+        ext[a] = bmax[a] - bmin[a];
+    }
+    candidate *cand = xmalloc(sizeof(candidate) * 3 * (size_t)nbins);
+    int ncand = 0;
+    for (int axis = 0; axis < 3; axis++) {
+        float e = ext[axis];
+        if (e < KD_EPS) {
+            continue;
+        }
+        float p = ext[(axis + 1) % 3], q = ext[(axis + 2) % 3];
+        for (int i = 0; i < nbins; i++) {
+            float d = (float)(i + 1) / (float)(nbins + 1);
+            candidate c;
+            c.axis = axis;
+            c.v = bmin[axis] + d * e;
+            c.SL0 = 2 * (p * q + e * d * (p + q));
+            c.SR0 = 2 * (p * q + e * (1 - d) * (p + q));
+            c.cost = INFINITY;
+            cand[ncand++] = c;
+        }
+    }
+    volatile float bound = INFINITY;
+    if (s.n >= 16384 && ncand > 1) {
+        /* big cell: candidates in parallel, shared pruning bound */
+#pragma omp taskloop grainsize(1) shared(cand, bound, s) default(none) firstprivate(ncand)
+        for (int k = 0; k < ncand; k++) {
+            float c = plane_cost(&s, cand[k].axis, cand[k].v, cand[k].SL0,
+                                 cand[k].SR0, &bound);
+            cand[k].cost = c;
+            if (c < bound) {
+#pragma omp critical(kd_bound)
+                if (c < bound) {
+                    bound = c;
+                }
+            }
+        }
+    } else {
+        for (int k = 0; k < ncand; k++) {
+            float c = plane_cost(&s, cand[k].axis, cand[k].v, cand[k].SL0,
+                                 cand[k].SR0, &bound);
+            cand[k].cost = c;
+            if (c < bound) {
+                bound = c;
+            }
+        }
+    }
+    /* first candidate attaining the minimum (strict '<' in the reference) */
+    int best = -1;
+    for (int k = 0; k < ncand; k++) {
+        if (best < 0 || cand[k].cost < cand[best].cost) {
+            /* a pruned candidate (inf) can only be taken as the very first */
+            best = k;
+        }
+    }
+    int ok = best >= 0;
+    float best_v = 0;
+    int best_axis = 0;
+    if (ok) {
+        best_v = cand[best].v;
+        best_axis = cand[best].axis;
+        if (best_v <= bmin[best_axis] || bmax[best_axis] <= best_v) {
+            ok = 0;
+        }
+    }
+    free(cand);
+    if (!ok) {
+        out = make_leaf(bmin, bmax, &s);
+        tri_set_free(&s);
+        return out;
+    }
+    /* partition: a vertex within EPS of the plane puts the triangle on both
+     * sides; comparisons in double (src/kd_tree.c:166-183) */
+    tri_set L = tri_set_alloc(s.n), R = tri_set_alloc(s.n);
+    double vL = (double)best_v + KD_EPS, vR = (double)best_v - KD_EPS;
+    const float *lo = s.lo[best_axis], *hi = s.hi[best_axis];
+    for (int t = 0; t < s.n; t++) {
+        if ((double)lo[t] <= vL) {
+            tri_set_push(&L, &s, t);
+        }
+        if ((double)hi[t] >= vR) {
+            tri_set_push(&R, &s, t);
+        }
+    }
+    int big = s.n >= 1024;
+    tri_set_free(&s);
+    float lmax[3], rmin[3];
+    memcpy(lmax, bmax, sizeof(lmax));
+    memcpy(rmin, bmin, sizeof(rmin));
+    lmax[best_axis] = rmin[best_axis] = best_v;
+
+    out = xmalloc(sizeof(*out));
+    memcpy(out->bmin, bmin, sizeof(out->bmin));
+    memcpy(out->bmax, bmax, sizeof(out->bmax));
+    out->leaf = 0;
+    out->value = best_v;
+    out->axis = best_axis;
+    out->ids = NULL;
+    out->nids = 0;
+    bnode *kl = NULL, *kr = NULL;
+#pragma omp task shared(kl) firstprivate(L, depth, nbins) if (big)
+    kl = build_cell(L, bmin, lmax, depth - 1, nbins);
+    kr = build_cell(R, rmin, bmax, depth - 1, nbins);
+#pragma omp taskwait
+    out->kid[0] = kl;
+    out->kid[1] = kr;
+    return out;
+}
+
+static void
+count_tree(const bnode *b, size_t *nodes, size_t *refs) {
+    /* iterative would need a stack of `depth`; recursion depth <= tree depth */
+    (*nodes)++;
+    if (b->leaf) {
+        *refs += (size_t)b->nids;
+        return;
+    }
+    count_tree(b->kid[0], nodes, refs);
+    count_tree(b->kid[1], nodes, refs);
+}
+
+typedef struct emitter {
+    kdnode *nodes;
+    int *refs;
+    int nnodes, nrefs;
+} emitter;
+
+static int
+emit_preorder(emitter *em, bnode *b) {
+    int me = em->nnodes++;
+    kdnode *n = &em->nodes[me];
+    memset(n, 0, sizeof(*n));
+    for (int a = 0; a < 3; a++) {
+        n->min.s[a] = b->bmin[a];
+        n->max.s[a] = b->bmax[a];
+    }
+    if (b->leaf) {
+        n->type = KD_LEAF;
+        n->leaf.tris = em->nrefs;
+        n->leaf.tri_count = b->nids;
+        for (int f = 0; f < 6; f++) {
+            n->leaf.ropes[f] = -1;
+        }
+        memcpy(em->refs + em->nrefs, b->ids, sizeof(int) * (size_t)b->nids);
+        em->nrefs += b->nids;
+        free(b->ids);
+    } else {
+        n->type = KD_SPLIT;
+        n->split.value = b->value;
+        n->split.axis = b->axis;
+        int l = emit_preorder(em, b->kid[0]);
+        int r = emit_preorder(em, b->kid[1]);
+        n = &em->nodes[me];
+        n->split.children[0] = l;
+        n->split.children[1] = r;
+    }
+    free(b);
+    return me;
+}
+
+/* Ropes (src/kd_tree.c:43-83).  Walking down from the root, each cell carries
+ * the six neighbour links of its box.  Before they are handed to the children
+ * every link is pushed down the neighbour's subtree for as long as the
+ * neighbour is split on an axis other than the face's own and the split plane
+ * does not cut this cell's extent on that axis; then the two children link to
+ * each other across the split plane. */
+static void
+push_down_link(const kdnode *nodes, const kdnode *cell, int face, int *link) {
+    while (*link != -1 && nodes[*link].type != KD_LEAF) {
+        const kdnode *nb = &nodes[*link];
+        int ax = nb->split.axis;
+        if (face / 2 == ax) {
+            return;
+        }
+        float plane = nb->split.value;
+        if (plane >= cell->max.s[ax]) {
+            *link = nb->split.children[0];
+        } else if (plane <= cell->min.s[ax]) {
+            *link = nb->split.children[1];
+        } else {
+            return;
+        }
+    }
+}
+
+static void
+link_cells(kdnode *nodes, int index, int links[6]) {
+    kdnode *cell = &nodes[index];
+    if (cell->type == KD_LEAF) {
+        memcpy(cell->leaf.ropes, links, sizeof(int) * 6);
+        return;
+    }
+    for (int f = 0; f < 6; f++) {
+        push_down_link(nodes, cell, f, &links[f]);
+    }
+    int ax = cell->split.axis;
+    int lo_child = cell->split.children[0], hi_child = cell->split.children[1];
+    int lo_links[6], hi_links[6];
+    memcpy(lo_links, links, sizeof(lo_links));
+    memcpy(hi_links, links, sizeof(hi_links));
+    lo_links[2 * ax + 1] = hi_child; /* max face of the low child */
+    hi_links[2 * ax] = lo_child;     /* min face of the high child */
+    link_cells(nodes, lo_child, lo_links);
+    link_cells(nodes, hi_child, hi_links);
+}
+
+int
+write_kd(const char *filename, const kd *tree) {
+    /* [size_t n][n records] for nodes(68) verts(16) norms(16) tri_indices(4)
+     * tris(16), host endian, no magic (src/kd_tree.c:250-271) */
+    FILE *f = fopen(filename, "wb");
+    if (f == NULL) {
+        perror(filename);
+        return 1;
+    }
+    const void *blk[5] = { tree->node_vec, tree->vert_vec, tree->norm_vec,
+                           tree->tri_indices, tree->tri_vec };
+    const size_t esz[5] = { sizeof(kdnode), sizeof(Vector4), sizeof(Vector4),
+                            sizeof(int), sizeof(cl_int3) };
+    int bad = 0;
+    for (int k = 0; k < 5 && !bad; k++) {
+        size_t n = blk[k] ? list_size(blk[k]) / esz[k] : 0;
+        bad |= fwrite(&n, sizeof(n), 1, f) != 1;
+        bad |= n && fwrite(blk[k], esz[k], n, f) != n;
+    }
+    bad |= fclose(f) != 0;
+    return bad;
+}
+
+int
+parse_kd(const char *filename, kd *tree) {
+    /* reader for the layout above (src/kd_tree.c:278-311); unlike the
+     * reference, I/O failures are reported instead of ignored */
+    FILE *f = fopen(filename, "rb");
+    if (f == NULL) {
+        perror(filename);
+        return 1;
+    }
+    void *blk[5] = { NULL, NULL, NULL, NULL, NULL };
+    const size_t esz[5] = { sizeof(kdnode), sizeof(Vector4), sizeof(Vector4),
+                            sizeof(int), sizeof(cl_int3) };
+    int bad = 0;
+    for (int k = 0; k < 5 && !bad; k++) {
+        size_t n = 0;
+        if (fread(&n, sizeof(n), 1, f) != 1) {
+            bad = 1;
+            break;
+        }
+        blk[k] = init_list(n, esz[k]);
+        if (n && fread(blk[k], esz[k], n, f) != n) {
+            bad = 1;
+        }
+    }
+    fclose(f);
+    if (bad) {
+        fprintf(stderr, "%s: truncated .kd file\n", filename);
+        for (int k = 0; k < 5; k++) {
+            delete_list(blk[k]);
+        }
+        return 1;
+    }
+    tree->node_vec = blk[0];
+    tree->vert_vec = blk[1];
+    tree->norm_vec = blk[2];
+    tree->tri_indices = blk[3];
+    tree->tri_vec = blk[4];
+    return 0;
+}
+
+void
+delete_kd(kd tree) {
+    delete_list(tree.node_vec);
+    delete_list(tree.tri_vec);
+    delete_list(tree.norm_vec);
+    delete_list(tree.vert_vec);
+    delete_list(tree.tri_indices);
+}
+
+static void
+depth_walk(const kdnode *nodes, int index, int depth, int *max_depth) {
+    if (depth > *max_depth) {
+        *max_depth = depth;
+    }
+    if (nodes[index].type == KD_SPLIT) {
+        depth_walk(nodes, nodes[index].split.children[0], depth + 1, max_depth);
+        depth_walk(nodes, nodes[index].split.children[1], depth + 1, max_depth);
+    }
+}
+
+void
+kd_get_stats(const kd *tree, kd_stats *out) {
+    memset(out, 0, sizeof(*out));
+    size_t n = vector_length(tree->node_vec);
+    out->node_count = (long long)n;
+    for (size_t i = 0; i < n; i++) {
+        const kdnode *k = &tree->node_vec[i];
+        if (k->type == KD_LEAF) {
+            out->leaf_count++;
+            out->leaf_tri_refs += k->leaf.tri_count;
+            out->empty_leaves += k->leaf.tri_count == 0;
+            if (k->leaf.tri_count > out->max_leaf_tris) {
+                out->max_leaf_tris = k->leaf.tri_count;
+            }
+        }
+    }
+    if (n) {
+        depth_walk(tree->node_vec, 0, 0, &out->max_depth);
+    }
+}
+
+kd
+build_kd_ex(cl_int3 *tris, Vector3 *verts, Vector3 *norms, const char *path,
+            int depth, int nbins) {
+    size_t ncorners = vector_length(tris);
+    size_t ntris = ncorners / 3;
+    kd tree = { NULL, NULL, verts, norms, tris };
+    if (ntris == 0) {
+        /* the reference would read verts[tris[0]] out of bounds here; emit a
+         * single empty leaf instead */
+        tree.node_vec = init_list(1, sizeof(kdnode));
+        memset(tree.node_vec, 0, sizeof(kdnode));
+        tree.node_vec[0].type = KD_LEAF;
+        for (int f = 0; f < 6; f++) {
+            tree.node_vec[0].leaf.ropes[f] = -1;
+        }
+        tree.tri_indices = new_list(0);
+        return tree;
+    }
+    tri_set root = tri_set_alloc((int)ntris);
+    Vector3 bmin, bmax;
+    bmin = bmax = verts[tris[0].s[0]];
+    for (size_t i = 0; i < ntris; i++) {
+        Vector3 A = verts[tris[3 * i + 0].s[0]], B = verts[tris[3 * i + 1].s[0]],
+                C = verts[tris[3 * i + 2].s[0]];
+        Vector3 tmin = vec_min(vec_min(A, B), C), tmax = vec_max(vec_max(A, B), C);
+        bmin = vec_min(bmin, tmin);
+        bmax = vec_max(bmax, tmax);
+        Vector3 N = vec_cross(vec_subtract(B, A), vec_subtract(C, A));
+        root.id[i] = (int)i;
+        for (int a = 0; a < 3; a++) {
+            root.lo[a][i] = tmin.s[a];
+            root.hi[a][i] = tmax.s[a];
+        }
+        root.area[i] = vec_length(N) / 2;
+    }
+    root.n = (int)ntris;
+
+    bnode *top = NULL;
+#pragma omp parallel
+#pragma omp single
+    top = build_cell(root, bmin.s, bmax.s, depth, nbins);
+
+    size_t nnodes = 0, nrefs = 0;
+    count_tree(top, &nnodes, &nrefs);
+    emitter em;
+    em.nodes = init_list(nnodes, sizeof(kdnode));
+    em.refs = init_list(nrefs, sizeof(int));
+    em.nnodes = em.nrefs = 0;
+    emit_preorder(&em, top);
+    int links[6] = { -1, -1, -1, -1, -1, -1 };
+    link_cells(em.nodes, 0, links);
+    tree.node_vec = em.nodes;
+    tree.tri_indices = em.refs;
+
+    if (path != NULL) {
+        size_t len = strlen(path) + 4;
+        char *kdpath = xmalloc(len);
+        snprintf(kdpath, len, "%s.kd", path);
+        write_kd(kdpath, &tree);
+        free(kdpath);
+    }
+    return tree;
+}
+
+kd
+build_kd(cl_int3 *tris, Vector3 *verts, Vector3 *norms, const char *path) {
+    return build_kd_ex(tris, verts, norms, path, KD_REF_DEPTH, KD_REF_NBINS);
+}

@@ -1,0 +1,154 @@
+/* CLState.h -- the render boundary, B200 edition.
+ *
+ * Drop-in for the reference's include/CLState.h:13-28: the same eight entry
+ * points with the same names, argument meaning, ownership and error
+ * behaviour, implemented with hand-written CUDA for sm_100a instead of an
+ * OpenCL kernel.  A caller written against the reference header (GLState.c is
+ * the only one, src/GLState.c:28-30,76-89,109,115,139-140) links against
+ * libclpt.so unchanged.
+ *
+ * Conventions kept from the reference:
+ *   - every function returns void; any device/runtime failure prints
+ *     "file:line: CUDA Error: NAME" to stderr and exit(EXIT_FAILURE)s
+ *     (include/error.h:3, src/error.c:147-154)
+ *   - single host thread, every call is synchronous; CLExecute returns when
+ *     the frame (and, multi-GPU, its gather) is complete (src/CLState.c:212)
+ *   - file-static singleton state (src/CLState.c:21-40)
+ *   - CLSetMeshes takes models[0]'s five host lists; CLTerminate frees them
+ *     (src/CLState.c:130,221-225)
+ *
+ * The "headless" block below has no counterpart in the reference, where the
+ * frame only ever lives in a GL texture: it adds a float4 framebuffer that can
+ * be read back, the render parameters the reference hard-codes, raw-pointer
+ * twins of the by-value/fat-pointer calls for FFI callers, timing, and the
+ * row-tile sharding used across GPUs.
+ */
+#ifndef CLSTATE_H
+#define CLSTATE_H
+
+#include <stddef.h>
+
+#include "clpt_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- the reference's eight (include/CLState.h:13-28) ---- */
+
+/* Bring the device up: pick the CUDA device (ordinal from CLSelectDevice or
+ * $CLPT_DEVICE, default 0 -- never a stdin prompt, unlike src/CLHandler.c:42-53),
+ * create the stream, the 64-byte camera buffer and default render parameters.
+ * Both arguments are accepted for source compatibility and ignored: the
+ * kernels are compiled into the library.  Replaces src/CLState.c:227-265. */
+void CLInit(const char *kernel_filename, const char *kernel_name);
+
+/* Free the host lists taken by CLSetMeshes and every device resource.
+ * Replaces src/CLState.c:221-225. */
+void CLTerminate(void);
+
+/* Blocking upload of the inverse camera matrix (row-major, rows[r].s[c]).
+ * Replaces src/CLState.c:67-79. */
+void CLSetCameraMatrix(Matrix matrix);
+
+/* Upload `size` BYTES of 24-byte packed Objects; no-op at size 0.  The
+ * reference uploads spheres but never intersects them (src/kernel.cl:199-225
+ * is unreferenced), and neither does this library: the slot exists for ABI
+ * compatibility.  Replaces src/CLState.c:104-122. */
+void CLSetObjects(Object *vec_objects, size_t size);
+
+/* Take models[0] (models is a list.c vector of kd; an empty vector is a
+ * no-op), re-pack its node array / tri_indices / tris / verts / norms into the
+ * device layout (DESIGN.md "data layout in HBM") and upload it.  Ownership of
+ * models[0]'s five lists passes to the library.  Replaces src/CLState.c:124-202. */
+void CLSetMeshes(kd *models);
+
+/* Release the current render target.  Replaces src/CLState.c:42-45. */
+void CLDeleteImage(void);
+
+/* Bind a GL_TEXTURE_2D (RGBA8) as the render target through
+ * cudaGraphicsGLRegisterImage.  Only available when the library is built with
+ * -DCLPT_WITH_GL (needs GL headers and a display; neither exists on the
+ * build/bench machines); otherwise it fails loudly.  Replaces src/CLState.c:47-58. */
+void CLCreateImage(unsigned int texture);
+
+/* Render one frame of width x height pixels with the current camera, scene
+ * and parameters into the render target, then synchronise.
+ * Replaces src/CLState.c:204-219. */
+void CLExecute(int width, int height);
+
+/* ---- headless additions ---- */
+
+enum {
+    CLPT_MODE_NORMAL = 0, /* as shipped: first-hit normal colour (src/kernel.cl:395-397) */
+    CLPT_MODE_MIRROR = 1, /* the dead code enabled: mirror bounces (src/kernel.cl:399-417) */
+    CLPT_MODE_PATH = 2    /* extension: diffuse/mirror materials, stochastic */
+};
+enum {
+    CLPT_FLAG_JITTER = 1,     /* sub-pixel jitter (implied by spp > 1 is NOT automatic: set it) */
+    CLPT_FLAG_ACCUMULATE = 2, /* progressive: add spp samples per frame into the target */
+    CLPT_FLAG_COUNTERS = 4    /* instrumented launch: fill the work counters */
+};
+
+typedef struct CLMaterial { /* 32 bytes */
+    float albedo[3];
+    int kind; /* 0 diffuse, 1 mirror */
+    float emission[3];
+    float pad;
+} CLMaterial;
+
+void CLSelectDevice(int ordinal);          /* before CLInit; default $CLPT_DEVICE or 0 */
+void CLSetCameraMatrixPtr(const Matrix *matrix);
+/* Like CLSetMeshes but from plain pointers + byte sizes; the data is copied,
+ * nothing is owned.  norms may be NULL / 0. */
+void CLSetMeshesRaw(const void *nodes, size_t node_bytes,
+                    const int *tri_indices, size_t tri_index_bytes,
+                    const void *tris, size_t tri_bytes,
+                    const void *verts, size_t vert_bytes,
+                    const void *norms, size_t norm_bytes);
+void CLSetMaterials(const CLMaterial *materials, size_t material_bytes,
+                    const int *tri_material, size_t tri_material_bytes);
+/* mode, depth (= bounces + 1; the reference passes 2, src/kernel.cl:468),
+ * samples per pixel per frame, RNG seed, CLPT_FLAG_* */
+void CLSetRenderParams(int mode, int depth, int spp, unsigned int seed, int flags);
+void CLSetMaxLeafVisits(int cap);          /* rope-hop cap per ray; default 4096 */
+void CLCreateImageHeadless(int width, int height); /* float4 target, zeroed */
+void CLResetAccumulation(void);            /* zero the target and the sample counter */
+/* Blocking device->host copy of the whole float4 frame (bytes must be
+ * width*height*16).  With CLPT_FLAG_ACCUMULATE the running sum is normalised
+ * by the sample count on the way out. */
+void CLReadImage(float *dst_rgba, size_t bytes);
+/* First-hit outputs of sample 0 of the last frame: primitive id (-1 miss),
+ * t, (u,v).  Any pointer may be NULL.  Only this rank's rows are valid when
+ * sharded. */
+void CLEnableAOV(int enable);
+void CLReadAOV(int *prim_id, float *t_hit, float *uv);
+/* rays, split visits, leaf visits, triangle tests, vn-shaded hits, capped
+ * rays of the last frame rendered with CLPT_FLAG_COUNTERS */
+void CLGetCounters(unsigned long long out[6]);
+float CLLastKernelMs(void);                /* device time of the last frame's render kernel */
+int CLLastLaunchCount(void);               /* kernels launched by the last CLExecute */
+/* CUDA events on the library's own stream, for callers that time many frames */
+void CLEventRecord(int slot);              /* slot 0..7 */
+float CLEventElapsedMs(int start_slot, int stop_slot); /* synchronises stop */
+void CLFlushL2(void);                      /* overwrite a buffer larger than L2 */
+
+/* ---- multi-GPU: one process per GPU, row tiles interleaved round-robin ----
+ * Rank r renders tiles t with t % nranks == r (tile = tile_rows image rows)
+ * into a compact slab; CLExecute then all-gathers the slabs with NCCL and
+ * de-interleaves into every rank's target.  The id is created on rank 0 with
+ * CLDistGetUniqueId and carried to the others by the caller. */
+void CLDistGetUniqueId(void *id128);       /* 128 bytes out */
+void CLDistInit(int rank, int nranks, const void *id128, int tile_rows);
+void CLDistShutdown(void);
+/* Sharding without a communicator (each rank keeps only its own rows). */
+void CLSetTileShard(int rank, int nranks, int tile_rows);
+
+const char *CLDeviceName(void);
+int CLDeviceSMCount(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* CLSTATE_H */

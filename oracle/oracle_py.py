@@ -1,0 +1,147 @@
+"""ctypes bindings for the checker libraries -- TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+``--impl reference`` legs import this.  Nothing under clpathtracer_b200/ does.
+
+  liboracle.so            CPU restatement of src/kernel.cl (oracle_kernel.c)
+  _ref/libref_host.so     the reference's own host code, compiled unmodified
+                          from /root/reference (Makefile target `ref`); present
+                          only where it was built
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+ORACLE_LIB = HERE / "liboracle.so"
+REF_LIB = HERE / "_ref" / "libref_host.so"
+
+FLAG_JITTER, FLAG_ACCUMULATE = 1, 2
+
+
+class OracleParams(C.Structure):
+    _fields_ = [
+        ("nodes", C.c_void_p), ("tri_indices", C.c_void_p), ("tris", C.c_void_p),
+        ("verts", C.c_void_p), ("norms", C.c_void_p), ("cam", C.c_void_p),
+        ("width", C.c_int32), ("height", C.c_int32), ("y0", C.c_int32), ("y1", C.c_int32),
+        ("mode", C.c_int32), ("depth", C.c_int32), ("spp", C.c_int32), ("flags", C.c_int32),
+        ("seed", C.c_uint32), ("sample_base", C.c_uint32),
+        ("max_leaf_visits", C.c_int32), ("threads", C.c_int32),
+        ("materials", C.c_void_p), ("tri_material", C.c_void_p),
+        ("n_materials", C.c_int32), ("reserved", C.c_int32),
+        ("rgba", C.c_void_p), ("prim_id", C.c_void_p), ("t_hit", C.c_void_p),
+        ("uv", C.c_void_p), ("normal", C.c_void_p),
+        ("counters", C.c_uint64 * 6),
+    ]
+
+
+_oracle = None
+_ref = None
+
+
+def build(force: bool = False) -> None:
+    if force or not ORACLE_LIB.exists():
+        subprocess.run(["make", "-s", "-C", str(HERE), "oracle"], check=True)
+
+
+def oracle() -> C.CDLL:
+    global _oracle
+    if _oracle is None:
+        build()
+        L = C.CDLL(str(ORACLE_LIB), mode=C.RTLD_LOCAL)
+        L.oracle_render.restype = C.c_int
+        L.oracle_render.argtypes = [C.POINTER(OracleParams)]
+        L.oracle_sizeof_params.restype = C.c_size_t
+        L.oracle_num_threads.restype = C.c_int
+        L.oracle_philox.restype = None
+        L.oracle_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        assert L.oracle_sizeof_params() == C.sizeof(OracleParams)
+        _oracle = L
+    return _oracle
+
+
+def have_ref() -> bool:
+    return REF_LIB.exists()
+
+
+def ref() -> C.CDLL:
+    """The reference's own host functions (list/vector/matrix/camera/kd_tree/model)."""
+    global _ref
+    if _ref is None:
+        L = C.CDLL(str(REF_LIB), mode=C.RTLD_LOCAL)
+        vp, sz = C.c_void_p, C.c_size_t
+        L.new_list.restype, L.new_list.argtypes = vp, [sz]
+        L.init_list.restype, L.init_list.argtypes = vp, [sz, sz]
+        L.list_size.restype, L.list_size.argtypes = sz, [vp]
+        L.delete_list.restype, L.delete_list.argtypes = None, [vp]
+        L.ref_cam_matrix_ptr.restype, L.ref_cam_matrix_ptr.argtypes = None, [vp, C.c_int, vp]
+        L.ref_sizeof_kdnode.restype = sz
+        L.ref_sizeof_camera.restype = sz
+        _ref = L
+    return _ref
+
+
+def philox(ctr, key) -> np.ndarray:
+    c = np.asarray(ctr, dtype=np.uint32)
+    k = np.asarray(key, dtype=np.uint32)
+    out = np.zeros(4, dtype=np.uint32)
+    oracle().oracle_philox(c.ctypes.data, k.ctypes.data, out.ctypes.data)
+    return out
+
+
+COUNTER_NAMES = ["rays", "splits", "leaves", "tris", "shade_vn", "capped"]
+
+
+def render(scene, cam: np.ndarray, width: int, height: int, mode: int = 0, depth: int = 2, spp: int = 1,
+           seed: int = 0, flags: int = 0, rows=None, threads: int = 0, max_leaf_visits: int = 4096,
+           materials: np.ndarray | None = None, tri_material: np.ndarray | None = None,
+           sample_base: int = 0, aov: bool = True, accumulate_into: np.ndarray | None = None) -> dict:
+    """Render with the CPU restatement.  `scene` has numpy members nodes (68-byte
+    records), tri_indices, tris (3t,4) int32, verts (v,4), norms (k,4) -- the wire
+    format.  Returns rgba (h,w,4), prim (h,w), t (h,w), uv (h,w,2), normal (h,w,3)
+    and the work counters."""
+    L = oracle()
+    P = OracleParams()
+    camf = np.ascontiguousarray(cam, dtype=np.float32).reshape(16)
+    keep = [camf]
+    P.nodes = scene.nodes.ctypes.data
+    P.tri_indices = scene.tri_indices.ctypes.data
+    P.tris = scene.tris.ctypes.data
+    P.verts = scene.verts.ctypes.data
+    P.norms = scene.norms.ctypes.data if len(scene.norms) else None
+    P.cam = camf.ctypes.data
+    P.width, P.height = width, height
+    P.y0, P.y1 = (0, height) if rows is None else rows
+    P.mode, P.depth, P.spp, P.flags = mode, depth, spp, flags
+    P.seed, P.sample_base = seed, sample_base
+    P.max_leaf_visits, P.threads = max_leaf_visits, threads
+    if materials is not None:
+        m = np.ascontiguousarray(materials, dtype=np.float32).reshape(-1, 8)
+        keep.append(m)
+        P.materials, P.n_materials = m.ctypes.data, len(m)
+        if tri_material is not None:
+            tm = np.ascontiguousarray(tri_material, dtype=np.int32)
+            keep.append(tm)
+            P.tri_material = tm.ctypes.data
+    out = {}
+    if accumulate_into is not None:
+        rgba = accumulate_into
+    else:
+        rgba = np.zeros((height, width, 4), dtype=np.float32)
+    out["rgba"] = rgba
+    P.rgba = rgba.ctypes.data
+    if aov:
+        out["prim"] = np.full((height, width), -1, dtype=np.int32)
+        out["t"] = np.zeros((height, width), dtype=np.float32)
+        out["uv"] = np.zeros((height, width, 2), dtype=np.float32)
+        out["normal"] = np.zeros((height, width, 3), dtype=np.float32)
+        P.prim_id, P.t_hit = out["prim"].ctypes.data, out["t"].ctypes.data
+        P.uv, P.normal = out["uv"].ctypes.data, out["normal"].ctypes.data
+    rc = L.oracle_render(C.byref(P))
+    assert rc == 0
+    out["counters"] = dict(zip(COUNTER_NAMES, [int(x) for x in P.counters]))
+    return out
