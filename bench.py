@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- the render hot path on BASELINE.json's headline workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU)
+
+Workload (BASELINE.json configs[2], the one the metric is quoted on): a
+1920x1080 frame, 64 jittered samples per pixel, primary + 4 mirror bounces
+(depth 5, the reference's bounce, src/kernel.cl:399-417) of the 999,698-triangle
+synthetic heightfield, canonical camera.  A "step" is one
+frame.  Rays = entries into the traversal loop (src/kernel.cl:311), counted on
+the device by an instrumented frame before timing.
+
+One JSON line on stdout (rank 0).  `value` = Mrays/s with everything resident
+in HBM (device events around CLExecute, max over ranks); `e2e` = the same
+metric through the C ABI with host buffers: camera upload, CLExecute and the
+float4 frame read back to pinned host memory inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "Mrays/s (primary+bounce) 1080p 1M-tri scene"
+UNIT = "Mrays/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--spp", type=int, default=64)
+    ap.add_argument("--depth", type=int, default=5, help="bounces + 1")
+    ap.add_argument("--grid", type=int, default=707, help="heightfield cells per side (707 -> 999,698 triangles)")
+    ap.add_argument("--tree-depth", type=int, default=int(os.environ.get("CLPT_TREE_DEPTH", "24")))
+    ap.add_argument("--tile-rows", type=int, default=8)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the baseline sample")
+    return ap.parse_args()
+
+
+def workload_config(a):
+    return {
+        "workload": f"{a.width}x{a.height}, {a.spp} spp jittered, {a.depth - 1} mirror bounces (depth {a.depth}), "
+                    f"heightfield n={a.grid} ({2 * a.grid * a.grid} triangles), kd depth {a.tree_depth}, canonical camera",
+        "width": a.width, "height": a.height, "spp": a.spp, "depth": a.depth, "triangles": 2 * a.grid * a.grid,
+        "kd_depth": a.tree_depth, "kd_bins": 25, "mode": "mirror (src/kernel.cl:399-417 enabled)",
+        "sharding": f"row tiles of {a.tile_rows} rows, round-robin over ranks, scene replicated, NCCL all-gather",
+        "l2": "flushed between timed frames (CLFlushL2, 256 MiB overwrite, outside the timed events)",
+    }
+
+
+def make_scene(a):
+    import clpathtracer_b200 as cl
+    from clpathtracer_b200 import scenes
+
+    t0 = time.time()
+    v, c, n = scenes.heightfield(a.grid, False)
+    t1 = time.time()
+    scene = cl.build_kd(v, c, n, depth=a.tree_depth)
+    t2 = time.time()
+    cam = cl.cam_matrix(cl.make_camera(**scenes.CANONICAL_CAMERA), a.height)
+    return scene, cam, {"scene_gen_s": round(t1 - t0, 2), "kd_build_s": round(t2 - t1, 2), **scene.stats()}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with NVML while the timed region runs."""
+
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag = index, threading.Event()
+        self.sm, self.reasons, self.max_mhz, self.err = [], set(), None, None
+
+    def run(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.stop_flag.is_set():
+                self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.05)
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def result(self):
+        self.stop_flag.set()
+        self.join(timeout=2)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "error": self.err}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.sm)}
+
+
+def algorithmic_bytes(counters, pixels):
+    """16 B per split visit, 36 B per leaf visit, 40 B per
+    triangle test, 36 B per vn-shaded hit, 16 B per pixel stored."""
+    return (16 * counters["splits"] + 36 * counters["leaves"] + 40 * counters["tris"] + 36 * counters["shade_vn"]
+            + 16 * pixels)
+
+
+def hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(a, scene, cam, target_seconds):
+    """The oracle port on this box's host cores, on a bounded sample of the same
+    workload: the same frame at fewer samples per pixel."""
+    from oracle import oracle_py as op
+
+    cores = op.oracle().oracle_num_threads()
+    kw = dict(mode=1, depth=a.depth, seed=a.seed, flags=op.FLAG_JITTER, aov=False)
+    t0 = time.time()
+    r = op.render(scene, cam, a.width, a.height, spp=1, **kw)
+    t1 = time.time() - t0
+    spp, rays, secs = 1, r["counters"]["rays"], t1
+    more = int(min(a.spp, target_seconds / max(t1, 1e-3)))
+    if more >= 2:
+        t0 = time.time()
+        r = op.render(scene, cam, a.width, a.height, spp=more, **kw)
+        secs, rays, spp = time.time() - t0, r["counters"]["rays"], more
+    return {"value": round(rays / secs / 1e6, 4), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"same scene/camera/depth, full {a.width}x{a.height} frame at {spp} of {a.spp} spp "
+                      f"({rays} rays in {secs:.1f} s)",
+            "ms_per_frame_at_full_spp": round(secs / spp * a.spp * 1e3, 1)}
+
+
+def run_reference(a):
+    """--impl reference: the reference's algorithm on the host cores.  kernel.cl
+    cannot be compiled here (no OpenCL), so this is the oracle port (kind 'port'),
+    all host threads, each step one full frame at 1 spp of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle_py as op
+
+    scene, cam, info = make_scene(a)
+    cores = op.oracle().oracle_num_threads()
+    kw = dict(mode=1, depth=a.depth, spp=1, flags=op.FLAG_JITTER, aov=False)
+    for w in range(a.warmup):
+        op.render(scene, cam, a.width, a.height, seed=a.seed, sample_base=w, **kw)
+    rays, t0 = 0, time.time()
+    for k in range(a.steps):
+        rays += op.render(scene, cam, a.width, a.height, seed=a.seed, sample_base=k, **kw)["counters"]["rays"]
+    secs = time.time() - t0
+    value = rays / secs / 1e6
+    sample = f"each step = the full {a.width}x{a.height} frame at 1 of {a.spp} spp, depth {a.depth}"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(secs / a.steps * 1e3, 2),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a),
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "scene": info,
+    }))
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import torch
+    import torch.distributed as dist
+
+    import clpathtracer_b200 as cl
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+        a.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the render path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    scene, cam, info = make_scene(a)
+    L = cl.lib()
+    r = cl.Renderer(device=local)
+    r.set_meshes(scene)
+    r.set_camera_matrix(cam)
+    if world > 1:
+        # the NCCL id is made by rank 0 and carried over torch.distributed (plumbing only)
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            raw = (np.zeros(128, dtype=np.uint8))
+            L.CLDistGetUniqueId(raw.ctypes.data)
+            idbuf = torch.from_numpy(raw.copy())
+        idbuf = idbuf.cuda()
+        dist.broadcast(idbuf, 0)
+        raw = idbuf.cpu().numpy().copy()
+        L.CLDistInit(rank, world, raw.ctypes.data, a.tile_rows)
+    r.create_image(a.width, a.height)
+    flags = cl.FLAG_JITTER
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # instrumented frame: counts rays / node / triangle work for this rank's rows
+    r.set_params(mode=cl.MODE_MIRROR, depth=a.depth, spp=a.spp, seed=a.seed, flags=flags | cl.FLAG_COUNTERS)
+    r.execute()
+    counters = r.counters()
+    r.set_params(mode=cl.MODE_MIRROR, depth=a.depth, spp=a.spp, seed=a.seed, flags=flags)
+    totals = torch.tensor([counters[k] for k in ("rays", "splits", "leaves", "tris", "shade_vn", "capped")],
+                          dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(totals)
+    tot = dict(zip(("rays", "splits", "leaves", "tris", "shade_vn", "capped"), [int(x) for x in totals.tolist()]))
+    rays_per_frame = tot["rays"]
+
+    for _ in range(max(a.warmup, 3)):
+        r.execute()
+
+    # ---- timed: device-resident ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    wall0 = time.time()
+    step_ms, kern_ms = [], []
+    for _ in range(a.steps):
+        L.CLFlushL2()
+        if world > 1:
+            dist.barrier()
+        L.CLEventRecord(0)
+        r.execute()
+        L.CLEventRecord(1)
+        step_ms.append(L.CLEventElapsedMs(0, 1))
+        kern_ms.append(r.kernel_ms())
+    barrier()
+    wall = time.time() - wall0
+    clocks = sampler.result()
+    launches = a.steps * L.CLLastLaunchCount()
+
+    # ---- timed: end to end through the C ABI with host buffers ----
+    host_frame = torch.empty((a.height, a.width, 4), dtype=torch.float32).pin_memory()
+    host_np = host_frame.numpy()
+    cam_host = np.ascontiguousarray(cam, dtype=np.float32)
+    barrier()
+    e2e_t0 = time.time()
+    for _ in range(a.steps):
+        r.set_camera_matrix(cam_host)   # 64 B host -> device (rides in the launch parameters)
+        r.execute()
+        r.read_image(host_np)           # float4 frame device -> pinned host
+    barrier()
+    e2e_s = time.time() - e2e_t0
+
+    t = torch.tensor([sum(step_ms), sum(kern_ms), e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, kernel_total_ms, e2e_ms = t.tolist()
+
+    if rank == 0:
+        ms_per_step = total_ms / a.steps
+        value = rays_per_frame / (ms_per_step * 1e-3) / 1e6
+        e2e_value = rays_per_frame / (e2e_ms / a.steps * 1e-3) / 1e6
+        peak, peak_src = hbm_peak()
+        # roofline of the render kernel: algorithmic bytes of ONE launch on this rank / its duration
+        my_bytes = algorithmic_bytes(counters, len(cl_rows(a, rank, world)) * a.width)
+        kernel_ms = float(np.mean(kern_ms))
+        achieved = my_bytes / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tp = ROOT / "profiles" / "traffic.json"
+        if tp.exists():
+            try:
+                traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        out = {
+            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a),
+            "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": 64,
+                    "d2h_bytes_per_step": a.width * a.height * 16, "ms_per_step": round(e2e_ms / a.steps, 4)},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "render_kernel<1,false>", "kernel_ms": round(kernel_ms, 4),
+                         "algorithmic_bytes_per_launch": my_bytes,
+                         "bytes_per_ray": round(my_bytes / max(counters["rays"], 1), 1)},
+            "rays_per_frame": rays_per_frame,
+            "work_per_ray": {k: round(tot[k] / max(tot["rays"], 1), 3) for k in ("splits", "leaves", "tris")},
+            "capped_rays": tot["capped"],
+            "ms_per_frame": round(ms_per_step, 4), "wall_ms_per_step_incl_flush": round(wall / a.steps * 1e3, 3),
+            "device": L.CLDeviceName().decode(), "scene": info,
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(a, scene, cam, a.cpu_seconds)
+        else:
+            out["cpu_baseline"] = None
+        print(json.dumps(out))
+    if world > 1:
+        L.CLDistShutdown()
+    r.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cl_rows(a, rank, world):
+    from clpathtracer_b200 import sharding
+
+    return sharding.rows_of_rank(a.height, rank, world, a.tile_rows)
+
+
+if __name__ == "__main__":
+    main()

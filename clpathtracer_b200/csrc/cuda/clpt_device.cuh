@@ -49,6 +49,7 @@ struct ClptFrame {
     float cam[16]; // row-major inverse camera matrix
     int width, height;
     int mode, depth, spp, flags;
+    int log2_sample_lanes;       // lanes per pixel = 1 << this (largest power of two <= min(spp, 32))
     unsigned int seed, sample_base;
     int max_leaf_visits;
     int rank, nranks, tile_rows; // row-tile sharding; nranks == 1 -> whole image

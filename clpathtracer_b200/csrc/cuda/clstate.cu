@@ -264,6 +264,8 @@ void clpt_state_launch_frame(int width, int height) {
     F.depth = St.depth;
     F.spp = St.spp;
     F.flags = St.flags;
+    F.log2_sample_lanes = 0;
+    while (F.log2_sample_lanes < 5 && (2 << F.log2_sample_lanes) <= St.spp) F.log2_sample_lanes++;
     F.seed = St.seed;
     F.sample_base = St.sample_base;
     F.max_leaf_visits = St.max_leaf_visits;

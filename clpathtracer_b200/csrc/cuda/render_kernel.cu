@@ -11,8 +11,8 @@
 // instead of global memory, split nodes are 8 bytes and siblings adjacent,
 // leaves are one aligned 64-byte record, triangles are pre-gathered per leaf
 // with the edge vectors precomputed, the hit normal is evaluated once per ray
-// instead of once per accepted candidate, the tail recursion is a loop, and
-// warps cover 8x4 pixel tiles.
+// instead of once per accepted candidate, the tail recursion is a loop, and the
+// lanes of a warp trace samples of the SAME pixel (see "Lane mapping" below).
 //
 // Numerics: every fp32 operation that decides a hit is written with the
 // round-to-nearest intrinsics (__fmul_rn, __fadd_rn, ...), which the compiler
@@ -31,6 +31,8 @@ __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b)
 __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+// 1/x: the correctly rounded reciprocal is the same number as the IEEE quotient 1.0f/x
+__device__ __forceinline__ float frcp(float a) { return __frcp_rn(a); }
 __device__ __forceinline__ V3 mk(float x, float y, float z) { V3 r = { x, y, z }; return r; }
 __device__ __forceinline__ V3 vadd(V3 a, V3 b) { return mk(fadd(a.x, b.x), fadd(a.y, b.y), fadd(a.z, b.z)); }
 __device__ __forceinline__ V3 vsub(V3 a, V3 b) { return mk(fsub(a.x, b.x), fsub(a.y, b.y), fsub(a.z, b.z)); }
@@ -72,7 +74,7 @@ __device__ __forceinline__ Hit closest_hit(const ClptScene &S, V3 o, V3 d, int m
     h.v = 0.0f;
     if (COUNT) cn.rays++;
 
-    const V3 inv = mk(fdiv(1.0f, d.x), fdiv(1.0f, d.y), fdiv(1.0f, d.z));
+    const V3 inv = mk(frcp(d.x), frcp(d.y), frcp(d.z));
     const bool sx = inv.x < 0.0f, sy = inv.y < 0.0f, sz = inv.z < 0.0f;
 
     float tmin, tmax;
@@ -127,7 +129,7 @@ __device__ __forceinline__ Hit closest_hit(const ClptScene &S, V3 o, V3 d, int m
             const V3 pvec = vcross(d, e2);
             const float det = vdot(e1, pvec);
             if (det < 0.0f) continue;
-            const float idet = fdiv(1.0f, det);
+            const float idet = frcp(det);
             const V3 tvec = vsub(o, xyz(a));
             const float u = fmul(vdot(tvec, pvec), idet);
             if (u < 0.0f || u > 1.0f) continue;
@@ -255,122 +257,149 @@ __device__ __forceinline__ V3 unproject(const float *M, V3 X) { // kernel.cl:89-
     return mk(fdiv(a, w), fdiv(b, w), fdiv(c, w));
 }
 
-// 256 threads = 8 warps; a warp is an 8x4 pixel tile, a block 32x8 pixels.
-constexpr int BLOCK_W = 32, BLOCK_H = 8;
+// Lane mapping.  A warp works on 32 / S pixels at a time, S lanes per pixel, where
+// S = sample_lanes = the largest power of two <= min(spp, 32): the S lanes of a
+// pixel trace S jittered samples of that pixel side by side, so the rays of a
+// warp share origin, leaves and triangles (warp-coherent by construction), node
+// and triangle loads collapse into broadcasts, and lanes finish together.  At
+// 1 spp this degenerates to one lane per pixel over an 8x4 pixel tile.
+//   pixels per warp   1     2     4     8     16    32
+//   warp tile (w x h) 1x1   2x1   2x2   4x2   4x4   8x4
+// A block is 8 warps laid out 4 x 2, i.e. (4*tw) x (2*th) pixels.
+// The samples of a pixel are summed in ascending sample order (shuffles in a
+// fixed order), which keeps the result independent of the mapping.
+__host__ __device__ inline void warp_tile_dims(int log2_ppw, int &tw, int &th) {
+    tw = 1 << ((log2_ppw + 1) >> 1);
+    th = 1 << (log2_ppw >> 1);
+}
+
+template <int MODE, bool COUNT>
+__device__ __forceinline__ V3 trace_sample(const ClptScene &S, const ClptFrame &F, int x, int y, unsigned pixel,
+                                           unsigned sample, bool write_aov, Counters &cn) {
+    const float *M = F.cam;
+    const V3 origin = mk(fdiv(M[2], M[14]), fdiv(M[6], M[14]), fdiv(M[10], M[14])); // :443-445
+    float fx = fsub((float)(unsigned)x, fdiv((float)(unsigned)F.width, 2.0f));
+    float fy = fsub((float)(unsigned)y, fdiv((float)(unsigned)F.height, 2.0f));
+    if (F.flags & CLPT_F_JITTER) {
+        unsigned c[4] = { pixel, sample, 0u, 0u };
+        philox(c, F.seed, CLPT_KEY1);
+        fx = fadd(fx, fsub(u01(c[0]), 0.5f));
+        fy = fadd(fy, fsub(u01(c[1]), 0.5f));
+    }
+    const V3 ncp = unproject(M, mk(fx, fy, -1.0f));
+    const V3 fcp = unproject(M, mk(fx, fy, 1.0f));
+    V3 o = origin;
+    V3 d = vnormalize(vsub(fcp, ncp));
+    if (MODE == 2) {
+        V3 Lsum = mk(0.0f, 0.0f, 0.0f), T = mk(1.0f, 1.0f, 1.0f);
+        for (int seg = 0; seg < F.depth; seg++) {
+            const Hit h = closest_hit<COUNT>(S, o, d, F.max_leaf_visits, cn);
+            if (seg == 0 && write_aov) {
+                const size_t px = (size_t)y * F.width + x;
+                F.aov_prim[px] = h.did_hit ? h.prim : -1;
+                F.aov_t[px] = h.did_hit ? h.t : 0.0f;
+                F.aov_uv[px] = make_float2(h.u, h.v);
+            }
+            if (!h.did_hit) {
+                Lsum = vadd(Lsum, T);
+                break;
+            }
+            const V3 nrm = hit_normal<COUNT>(S, h, cn);
+            float al[3] = { 0.5f, 0.5f, 0.5f }, em[3] = { 0.0f, 0.0f, 0.0f };
+            int kind = 0;
+            if (S.n_materials > 0) {
+                int m = S.tri_material ? __ldg(S.tri_material + h.prim) : 0;
+                if (m < 0 || m >= S.n_materials) m = 0;
+                const ClptMaterial *mp = S.materials + m;
+                al[0] = mp->albedo[0]; al[1] = mp->albedo[1]; al[2] = mp->albedo[2];
+                em[0] = mp->emission[0]; em[1] = mp->emission[1]; em[2] = mp->emission[2];
+                kind = mp->kind;
+            }
+            Lsum = vadd(Lsum, mk(fmul(T.x, em[0]), fmul(T.y, em[1]), fmul(T.z, em[2])));
+            T = mk(fmul(T.x, al[0]), fmul(T.y, al[1]), fmul(T.z, al[2]));
+            const V3 hp = vadd(o, vscale(d, h.t));
+            V3 nd;
+            if (kind == 1) {
+                nd = vnormalize(vsub(d, vscale(nrm, fmul(2.0f, vdot(d, nrm)))));
+            } else {
+                nd = cosine_dir(nrm, pixel, sample, (unsigned)seg, F.seed);
+            }
+            o = vadd(hp, vscale(nd, 0.0001f));
+            d = nd;
+        }
+        return Lsum;
+    }
+    // modes A/B: kernel.cl:296-422 with the tail recursion as a loop
+    V3 col = mk(0.0f, 0.0f, 0.0f);
+    float str = 1.0f;
+    int depth = F.depth;
+    if (MODE == 0) depth = depth > 0 ? 1 : 0;
+    const int first_depth = depth;
+    for (; depth > 0; depth--) {
+        const Hit h = closest_hit<COUNT>(S, o, d, F.max_leaf_visits, cn);
+        if (depth == first_depth && write_aov) {
+            const size_t px = (size_t)y * F.width + x;
+            F.aov_prim[px] = h.did_hit ? h.prim : -1;
+            F.aov_t[px] = h.did_hit ? h.t : 0.0f;
+            F.aov_uv[px] = make_float2(h.u, h.v);
+        }
+        if (!h.did_hit) break;
+        const V3 nrm = hit_normal<COUNT>(S, h, cn);
+        const V3 nc = mk(fdiv(fadd(nrm.x, 1.0f), 2.0f), fdiv(fadd(nrm.y, 1.0f), 2.0f),
+                         fdiv(fadd(nrm.z, 1.0f), 2.0f));
+        if (MODE == 0) return nc; // the `return` at :396
+        V3 no = vadd(o, vscale(d, h.t));
+        const V3 nd = vnormalize(vsub(d, vscale(nrm, fmul(2.0f, vdot(d, nrm)))));
+        no = vadd(no, vscale(nd, 0.0001f));
+        col = vadd(vscale(col, fsub(1.0f, str)), vscale(nc, str));
+        str = fmul(str, 0.2f);
+        o = no;
+        d = nd;
+    }
+    const float k = fsub(1.0f, str); // :421
+    return mk(fadd(fmul(k, col.x), str), fadd(fmul(k, col.y), str), fadd(fmul(k, col.z), str));
+}
 
 template <int MODE, bool COUNT>
 __global__ void __launch_bounds__(256)
 render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptFrame F) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x = blockIdx.x * BLOCK_W + (warp & 3) * 8 + (lane & 7);
-    const int ly = blockIdx.y * BLOCK_H + (warp >> 2) * 4 + (lane >> 3); // row within this rank's slab
+    const int log2_s = F.log2_sample_lanes, s_lanes = 1 << log2_s;
+    int tw, th;
+    warp_tile_dims(5 - log2_s, tw, th);
+    const int pslot = lane >> log2_s, sslot = lane & (s_lanes - 1);
+    const int x = (blockIdx.x * 4 + (warp & 3)) * tw + (pslot & (tw - 1));
+    // row within this rank's slab
+    const int ly = (blockIdx.y * 2 + (warp >> 2)) * th + pslot / tw;
     // slab row -> image row: tiles of tile_rows rows dealt round-robin to ranks
     const int lt = ly / F.tile_rows;
     const int y = (lt * F.nranks + F.rank) * F.tile_rows + (ly - lt * F.tile_rows);
+    const bool valid = x < F.width && y < F.height && ly < F.local_rows;
+    const unsigned pixel = (unsigned)(y * F.width + x);
+    const int spp = F.spp < 1 ? 1 : F.spp;
+    const int group_base = lane & ~(s_lanes - 1);
     Counters cn = { 0, 0, 0, 0, 0, 0 };
-    if (x < F.width && y < F.height && ly < F.local_rows) {
-        const float *M = F.cam;
-        const unsigned pixel = (unsigned)(y * F.width + x);
-        const V3 origin = mk(fdiv(M[2], M[14]), fdiv(M[6], M[14]), fdiv(M[10], M[14])); // :443-445
-        V3 acc = mk(0.0f, 0.0f, 0.0f);
-        const int spp = F.spp < 1 ? 1 : F.spp;
-        for (int s = 0; s < spp; s++) {
-            const unsigned sample = F.sample_base + (unsigned)s;
-            float fx = fsub((float)(unsigned)x, fdiv((float)(unsigned)F.width, 2.0f));
-            float fy = fsub((float)(unsigned)y, fdiv((float)(unsigned)F.height, 2.0f));
-            if (F.flags & CLPT_F_JITTER) {
-                unsigned c[4] = { pixel, sample, 0u, 0u };
-                philox(c, F.seed, CLPT_KEY1);
-                fx = fadd(fx, fsub(u01(c[0]), 0.5f));
-                fy = fadd(fy, fsub(u01(c[1]), 0.5f));
-            }
-            const V3 ncp = unproject(M, mk(fx, fy, -1.0f));
-            const V3 fcp = unproject(M, mk(fx, fy, 1.0f));
-            V3 o = origin;
-            V3 d = vnormalize(vsub(fcp, ncp));
-            V3 colour;
-            if (MODE == 2) {
-                V3 Lsum = mk(0.0f, 0.0f, 0.0f), T = mk(1.0f, 1.0f, 1.0f);
-                for (int seg = 0; seg < F.depth; seg++) {
-                    const Hit h = closest_hit<COUNT>(S, o, d, F.max_leaf_visits, cn);
-                    if (seg == 0 && s == 0 && F.aov_prim) {
-                        const size_t px = (size_t)y * F.width + x;
-                        F.aov_prim[px] = h.did_hit ? h.prim : -1;
-                        F.aov_t[px] = h.did_hit ? h.t : 0.0f;
-                        F.aov_uv[px] = make_float2(h.u, h.v);
-                    }
-                    if (!h.did_hit) {
-                        Lsum = vadd(Lsum, T);
-                        break;
-                    }
-                    const V3 nrm = hit_normal<COUNT>(S, h, cn);
-                    float al[3] = { 0.5f, 0.5f, 0.5f }, em[3] = { 0.0f, 0.0f, 0.0f };
-                    int kind = 0;
-                    if (S.n_materials > 0) {
-                        int m = S.tri_material ? __ldg(S.tri_material + h.prim) : 0;
-                        if (m < 0 || m >= S.n_materials) m = 0;
-                        const ClptMaterial *mp = S.materials + m;
-                        al[0] = mp->albedo[0]; al[1] = mp->albedo[1]; al[2] = mp->albedo[2];
-                        em[0] = mp->emission[0]; em[1] = mp->emission[1]; em[2] = mp->emission[2];
-                        kind = mp->kind;
-                    }
-                    Lsum = vadd(Lsum, mk(fmul(T.x, em[0]), fmul(T.y, em[1]), fmul(T.z, em[2])));
-                    T = mk(fmul(T.x, al[0]), fmul(T.y, al[1]), fmul(T.z, al[2]));
-                    V3 hp = vadd(o, vscale(d, h.t));
-                    V3 nd;
-                    if (kind == 1) {
-                        nd = vnormalize(vsub(d, vscale(nrm, fmul(2.0f, vdot(d, nrm)))));
-                    } else {
-                        nd = cosine_dir(nrm, pixel, sample, (unsigned)seg, F.seed);
-                    }
-                    o = vadd(hp, vscale(nd, 0.0001f));
-                    d = nd;
-                }
-                colour = Lsum;
-            } else {
-                // modes A/B: kernel.cl:296-422 with the tail recursion as a loop
-                V3 col = mk(0.0f, 0.0f, 0.0f);
-                float str = 1.0f;
-                bool done = false;
-                int depth = F.depth;
-                if (MODE == 0) depth = depth > 0 ? 1 : 0;
-                colour = col;
-                for (; depth > 0; depth--) {
-                    const Hit h = closest_hit<COUNT>(S, o, d, F.max_leaf_visits, cn);
-                    if (depth == (MODE == 0 ? 1 : F.depth) && s == 0 && F.aov_prim) {
-                        const size_t px = (size_t)y * F.width + x;
-                        F.aov_prim[px] = h.did_hit ? h.prim : -1;
-                        F.aov_t[px] = h.did_hit ? h.t : 0.0f;
-                        F.aov_uv[px] = make_float2(h.u, h.v);
-                    }
-                    if (!h.did_hit) break;
-                    const V3 nrm = hit_normal<COUNT>(S, h, cn);
-                    const V3 nc = mk(fdiv(fadd(nrm.x, 1.0f), 2.0f), fdiv(fadd(nrm.y, 1.0f), 2.0f),
-                                     fdiv(fadd(nrm.z, 1.0f), 2.0f));
-                    if (MODE == 0) { // the `return` at :396
-                        colour = nc;
-                        done = true;
-                        break;
-                    }
-                    V3 no = vadd(o, vscale(d, h.t));
-                    const V3 nd = vnormalize(vsub(d, vscale(nrm, fmul(2.0f, vdot(d, nrm)))));
-                    no = vadd(no, vscale(nd, 0.0001f));
-                    col = vadd(vscale(col, fsub(1.0f, str)), vscale(nc, str));
-                    str = fmul(str, 0.2f);
-                    o = no;
-                    d = nd;
-                }
-                if (!done) { // :421
-                    const float k = fsub(1.0f, str);
-                    colour = mk(fadd(fmul(k, col.x), str), fadd(fmul(k, col.y), str),
-                                fadd(fmul(k, col.z), str));
-                }
-            }
-            acc = vadd(acc, colour);
+    V3 acc = mk(0.0f, 0.0f, 0.0f);
+    for (int base = 0; base < spp; base += s_lanes) {
+        const int s = base + sslot;
+        V3 colour = mk(0.0f, 0.0f, 0.0f);
+        if (valid && s < spp) {
+            colour = trace_sample<MODE, COUNT>(S, F, x, y, pixel, F.sample_base + (unsigned)s,
+                                               s == 0 && F.aov_prim != nullptr, cn);
         }
+        // ordered sum over the samples of this round (every lane of the group
+        // computes the same running sum)
+        for (int j = 0; j < s_lanes; j++) {
+            const float cx = __shfl_sync(0xffffffffu, colour.x, group_base + j);
+            const float cy = __shfl_sync(0xffffffffu, colour.y, group_base + j);
+            const float cz = __shfl_sync(0xffffffffu, colour.z, group_base + j);
+            if (base + j < spp) acc = vadd(acc, mk(cx, cy, cz));
+        }
+    }
+    if (valid && sslot == 0) {
         float4 *dst = F.target + (size_t)ly * F.width + x;
         if (F.flags & CLPT_F_ACCUMULATE) {
-            float4 prev = *dst;
+            const float4 prev = *dst;
             *dst = make_float4(fadd(prev.x, acc.x), fadd(prev.y, acc.y), fadd(prev.z, acc.z),
                                fadd(prev.w, (float)spp));
         } else if (spp == 1) {
@@ -384,9 +413,9 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
         unsigned v[6] = { cn.rays, cn.splits, cn.leaves, cn.tris, cn.shade_vn, cn.capped };
 #pragma unroll
         for (int k = 0; k < 6; k++) {
-            unsigned s = v[k];
-            for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
-            if (lane == 0 && s) atomicAdd(F.counters + k, (unsigned long long)s);
+            unsigned sum = v[k];
+            for (int off = 16; off > 0; off >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, off);
+            if (lane == 0 && sum) atomicAdd(F.counters + k, (unsigned long long)sum);
         }
     }
 }
@@ -433,7 +462,10 @@ void launch_mode(const ClptScene &scene, const ClptFrame &frame, dim3 grid, cuda
 } // namespace
 
 void clpt_launch_render(const ClptScene &scene, const ClptFrame &frame, cudaStream_t stream) {
-    dim3 grid((frame.width + BLOCK_W - 1) / BLOCK_W, (frame.local_rows + BLOCK_H - 1) / BLOCK_H);
+    int tw, th;
+    warp_tile_dims(5 - frame.log2_sample_lanes, tw, th);
+    const int block_w = 4 * tw, block_h = 2 * th;
+    dim3 grid((frame.width + block_w - 1) / block_w, (frame.local_rows + block_h - 1) / block_h);
     if (grid.x == 0 || grid.y == 0) return;
     switch (frame.mode) {
     case 0: launch_mode<0>(scene, frame, grid, stream); break;

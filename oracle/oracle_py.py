@@ -145,3 +145,62 @@ def render(scene, cam: np.ndarray, width: int, height: int, mode: int = 0, depth
     assert rc == 0
     out["counters"] = dict(zip(COUNTER_NAMES, [int(x) for x in P.counters]))
     return out
+
+
+# ---------------------------------------------------------------- Harness C
+# The reference's own kernel.cl through an OpenCL ICD (cl_harness.c).
+REF_KERNEL_LIB = HERE / "_ref" / "libref_kernel.so"
+_refk = None
+
+
+def _ref_kernel():
+    global _refk
+    if _refk is None:
+        import os
+
+        if "OCL_ICD_FILENAMES" not in os.environ and "OCL_ICD_VENDORS" not in os.environ:
+            for cand in ("/usr/lib/libnvidia-opencl.so.1", "/usr/local/nvidia/lib/libnvidia-opencl.so.1",
+                         "/usr/lib/x86_64-linux-gnu/libnvidia-opencl.so.1"):
+                if Path(cand).exists():
+                    os.environ["OCL_ICD_FILENAMES"] = cand
+                    break
+        L = C.CDLL(str(REF_KERNEL_LIB), mode=C.RTLD_LOCAL)
+        L.refcl_available.restype, L.refcl_available.argtypes = C.c_int, [C.c_char_p, C.c_int]
+        L.refcl_render.restype = C.c_int
+        L.refcl_render.argtypes = [C.c_void_p, C.c_size_t] * 5 + [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                                                 C.POINTER(C.c_double), C.c_char_p, C.c_int]
+        L.refcl_build_options.restype = C.c_char_p
+        _refk = L
+    return _refk
+
+
+def ref_kernel_available() -> tuple[bool, str]:
+    """(usable, 'platform / device' or the reason it is not)."""
+    if not REF_KERNEL_LIB.exists():
+        return False, "oracle/_ref/libref_kernel.so not built (needs /root/reference at build time)"
+    msg = C.create_string_buffer(512)
+    rc = _ref_kernel().refcl_available(msg, 512)
+    return rc == 0, msg.value.decode(errors="replace")
+
+
+def ref_kernel_render(scene, cam: np.ndarray, width: int, height: int, repeats: int = 1):
+    """One frame of the UNMODIFIED reference kernel (as shipped: first-hit normal
+    colour).  Returns (rgba float32[h,w,4], kernel_ms)."""
+    L = _ref_kernel()
+    camf = np.ascontiguousarray(cam, dtype=np.float32).reshape(16)
+    out = np.zeros((height, width, 4), dtype=np.float32)
+    ms = C.c_double(0)
+    log = C.create_string_buffer(16384)
+    norms = scene.norms if len(scene.norms) else None
+    rc = L.refcl_render(scene.nodes.ctypes.data, scene.nodes.nbytes, scene.tri_indices.ctypes.data,
+                        scene.tri_indices.nbytes, scene.tris.ctypes.data, scene.tris.nbytes,
+                        scene.verts.ctypes.data, scene.verts.nbytes,
+                        None if norms is None else norms.ctypes.data, 0 if norms is None else norms.nbytes,
+                        camf.ctypes.data, width, height, repeats, out.ctypes.data, C.byref(ms), log, 16384)
+    if rc != 0:
+        raise RuntimeError("reference kernel run failed: " + log.value.decode(errors="replace"))
+    return out, ms.value
+
+
+def ref_kernel_build_options() -> str:
+    return _ref_kernel().refcl_build_options().decode()

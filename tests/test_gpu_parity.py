@@ -1,0 +1,293 @@
+"""Parity of the CUDA render path (through the C ABI) with the oracle.
+
+Every test drives libclpt.so through the CLState entry points and compares with
+oracle/oracle_kernel.c on the same scene, camera and seed.  Bars (SURVEY.md
+section 8d): first-hit primitive ids, t, (u,v) and colours BIT-EXACT for the
+deterministic modes (both sides evaluate the same fp32 expressions in the same
+order without FMA contraction); the stochastic extension is compared with the
+same Philox streams and must also be bit-exact; the north-star's looser bound
+(mean abs error < 1e-3 at 1 spp) is asserted as well, with the tolerance
+written here.
+"""
+import ctypes as C
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+MAE_TOL = 1e-3  # north-star tolerance for accumulated radiance at 1 spp
+
+
+def _cam(clpt, which, height):
+    from clpathtracer_b200 import scenes
+
+    kw = {"canonical": scenes.CANONICAL_CAMERA, "reference": scenes.REFERENCE_CAMERA,
+          "cornell": scenes.CORNELL_CAMERA}[which]
+    return clpt.cam_matrix(clpt.make_camera(**kw), height)
+
+
+def _render_gpu(r, scene, cam, w, h, aov=True, **params):
+    r.set_meshes(scene)
+    r.set_camera_matrix(cam)
+    r.set_params(**params)
+    r.create_image(w, h, aov=aov)
+    r.execute()
+    img = r.read_image()
+    return (img,) + (r.read_aov() if aov else ())
+
+
+def _assert_bit_equal(a, b, what):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    same = a.view(np.uint32) == b.view(np.uint32)
+    assert same.all(), f"{what}: {np.count_nonzero(~same)} of {same.size} words differ"
+
+
+CASES = [
+    # scene, camera, w, h, mode, depth
+    ("hf22n", "canonical", 640, 480, 0, 2),   # BASELINE config 1 size, as shipped
+    ("hf22n", "canonical", 640, 480, 1, 2),   # primary + 1 mirror bounce
+    ("hf22", "canonical", 320, 240, 0, 2),    # flat normals (no vn)
+    ("hf22", "canonical", 320, 240, 1, 5),
+    ("hf22n", "reference", 333, 197, 1, 3),   # odd sizes, camera inside the scene box
+    ("cornell", "cornell", 640, 480, 0, 2),
+    ("cornell", "cornell", 640, 480, 1, 5),
+    ("soup3000", "cornell", 256, 256, 1, 4),  # incoherent
+    ("hf224", "canonical", 480, 270, 1, 2),   # 100k triangles
+]
+
+
+@pytest.mark.parametrize("name,camera,w,h,mode,depth", CASES)
+def test_deterministic_modes_bit_exact(clpt, oracle, renderer, scene_cache, name, camera, w, h, mode, depth):
+    scene, _ = scene_cache(name)
+    cam = _cam(clpt, camera, h)
+    img, prim, t, uv = _render_gpu(renderer, scene, cam, w, h, mode=mode, depth=depth)
+    ref = oracle.render(scene, cam, w, h, mode=mode, depth=depth)
+    assert np.array_equal(prim, ref["prim"]), f"{np.count_nonzero(prim != ref['prim'])} primitive ids differ"
+    _assert_bit_equal(t, ref["t"], "t")
+    _assert_bit_equal(uv, ref["uv"], "uv")
+    _assert_bit_equal(img, ref["rgba"], "rgba")
+    assert np.abs(img - ref["rgba"]).mean() < MAE_TOL
+    assert (prim >= 0).mean() > (0.01 if name.startswith('soup') else 0.05)  # the camera sees the scene
+
+
+@pytest.mark.parametrize("depth_tree", [8, 20, 24])
+def test_other_tree_depths(clpt, oracle, renderer, depth_tree):
+    """The traversal is tree-agnostic: shallow and deep trees of the same mesh."""
+    from clpathtracer_b200 import scenes
+
+    v, c, n = scenes.heightfield(100, False)
+    scene = clpt.build_kd(v, c, n, depth=depth_tree)
+    cam = _cam(clpt, "canonical", 270)
+    img, prim, t, uv = _render_gpu(renderer, scene, cam, 480, 270, mode=1, depth=3)
+    ref = oracle.render(scene, cam, 480, 270, mode=1, depth=3)
+    assert np.array_equal(prim, ref["prim"])
+    _assert_bit_equal(t, ref["t"], "t")
+    _assert_bit_equal(img, ref["rgba"], "rgba")
+
+
+def test_counters_match_oracle(clpt, oracle, renderer, scene_cache):
+    """Same leaves, same triangles, same order: the work counters are equal."""
+    scene, _ = scene_cache("hf22n")
+    cam = _cam(clpt, "canonical", 480)
+    _render_gpu(renderer, scene, cam, 640, 480, mode=1, depth=2, flags=clpt.FLAG_COUNTERS)
+    got = renderer.counters()
+    want = oracle.render(scene, cam, 640, 480, mode=1, depth=2)["counters"]
+    assert got == want
+    # SURVEY.md section 6 figures for this scene/camera, as shipped
+    _render_gpu(renderer, scene, cam, 640, 480, mode=0, depth=2, flags=clpt.FLAG_COUNTERS)
+    got = renderer.counters()
+    assert got["rays"] == 307200
+    assert round(got["splits"] / got["rays"], 2) == 12.55 and round(got["tris"] / got["rays"], 2) == 5.17
+
+
+def test_jittered_multisample(clpt, oracle, renderer, scene_cache):
+    scene, _ = scene_cache("hf22n")
+    cam = _cam(clpt, "canonical", 240)
+    kw = dict(mode=1, depth=3, spp=8, seed=1234, flags=clpt.FLAG_JITTER)
+    img, prim, t, uv = _render_gpu(renderer, scene, cam, 320, 240, **kw)
+    ref = oracle.render(scene, cam, 320, 240, **kw)
+    assert np.array_equal(prim, ref["prim"])
+    _assert_bit_equal(img, ref["rgba"], "rgba")
+    # a different seed gives a different image; the same seed the same image
+    img2 = _render_gpu(renderer, scene, cam, 320, 240, **dict(kw, seed=99))[0]
+    assert not np.array_equal(img, img2)
+    img3 = _render_gpu(renderer, scene, cam, 320, 240, **kw)[0]
+    assert np.array_equal(img, img3)
+    # spp == 1 without jitter is the reference's own ray generation
+    a = _render_gpu(renderer, scene, cam, 320, 240, mode=1, depth=3, spp=1, seed=5)[0]
+    b = _render_gpu(renderer, scene, cam, 320, 240, mode=1, depth=3, spp=1, seed=77)[0]
+    assert np.array_equal(a, b)
+
+
+def test_path_mode_extension(clpt, oracle, renderer, scene_cache):
+    """Mode C (no reference behaviour): identical Philox streams -> identical images."""
+    from clpathtracer_b200 import scenes
+
+    scene, extra = scene_cache("cornell")
+    cam = _cam(clpt, "cornell", 240)
+    renderer.set_meshes(scene)
+    renderer.set_materials(scenes.CORNELL_MATERIALS, extra["tri_material"])
+    renderer.set_camera_matrix(cam)
+    kw = dict(mode=2, depth=4, spp=4, seed=7, flags=clpt.FLAG_JITTER)
+    renderer.set_params(**kw)
+    renderer.create_image(320, 240, aov=True)
+    renderer.execute()
+    img = renderer.read_image()
+    ref = oracle.render(scene, cam, 320, 240, materials=scenes.CORNELL_MATERIALS,
+                        tri_material=extra["tri_material"], **kw)
+    _assert_bit_equal(img, ref["rgba"], "rgba")
+    assert np.abs(img - ref["rgba"]).mean() < MAE_TOL
+    assert img[..., :3].max() > 1.0  # the light is visible
+    # degrade: mirror materials at 1 spp without jitter reproduce the mirror geometry of mode B
+    mirror = np.array([[1, 1, 1, 0, 0, 0, 0, 0]], dtype=np.float32)
+    mirror.view(np.int32)[0, 3] = 1
+    renderer.set_materials(mirror, None)
+    renderer.set_params(mode=2, depth=3, spp=1, seed=0, flags=0)
+    renderer.execute()
+    ref = oracle.render(scene, cam, 320, 240, mode=2, depth=3, materials=mirror)
+    _assert_bit_equal(renderer.read_image(), ref["rgba"], "mirror path rgba")
+
+
+def test_progressive_accumulation(clpt, oracle, renderer, scene_cache):
+    scene, _ = scene_cache("hf22n")
+    cam = _cam(clpt, "canonical", 120)
+    flags = clpt.FLAG_JITTER | clpt.FLAG_ACCUMULATE
+    renderer.set_meshes(scene)
+    renderer.set_camera_matrix(cam)
+    renderer.set_params(mode=1, depth=2, spp=2, seed=3, flags=flags)
+    renderer.create_image(160, 120)
+    acc = np.zeros((120, 160, 4), dtype=np.float32)
+    for frame in range(3):
+        renderer.execute()
+        oracle.render(scene, cam, 160, 120, mode=1, depth=2, spp=2, seed=3, flags=flags, sample_base=2 * frame,
+                      accumulate_into=acc, aov=False)
+    img = renderer.read_image()
+    want = acc.copy()
+    want[..., :3] = acc[..., :3] * (np.float32(1.0) / acc[..., 3:4])
+    want[..., 3] = 1.0
+    _assert_bit_equal(img, want, "accumulated rgba")
+    clpt.lib().CLResetAccumulation()
+    renderer.execute()
+    one = renderer.read_image()
+    ref = oracle.render(scene, cam, 160, 120, mode=1, depth=2, spp=2, seed=3, flags=clpt.FLAG_JITTER)
+    _assert_bit_equal(one, ref["rgba"], "after reset")
+    renderer.set_params()
+
+
+@pytest.mark.parametrize("nranks,tile_rows", [(2, 8), (3, 16), (8, 8)])
+def test_row_tile_sharding(clpt, oracle, renderer, scene_cache, nranks, tile_rows):
+    """Each rank's rows, rendered separately, are exactly those rows of the full frame."""
+    scene, _ = scene_cache("hf22n")
+    w, h = 200, 150
+    cam = _cam(clpt, "canonical", h)
+    full = oracle.render(scene, cam, w, h, mode=1, depth=3)["rgba"]
+    L = clpt.lib()
+    seen = np.zeros(h, dtype=int)
+    try:
+        for rank in range(nranks):
+            renderer.set_meshes(scene)
+            renderer.set_camera_matrix(cam)
+            renderer.set_params(mode=1, depth=3)
+            renderer.create_image(w, h)
+            L.CLSetTileShard(rank, nranks, tile_rows)
+            renderer.execute()
+            img = renderer.read_image()
+            rows = np.array([y for y in range(h) if (y // tile_rows) % nranks == rank], dtype=int)
+            seen[rows] += 1
+            _assert_bit_equal(img[rows], full[rows], f"rank {rank} rows")
+            others = np.setdiff1d(np.arange(h), rows)
+            assert not img[others].any()  # untouched without a communicator
+    finally:
+        L.CLSetTileShard(0, 1, 8)
+    assert (seen == 1).all()
+
+
+def test_owned_meshes_and_object_slot(clpt, oracle, renderer, scene_cache):
+    """The reference's own CLSetMeshes(kd*) ownership path and the no-op object slot."""
+    scene, _ = scene_cache("hf22")
+    cam = _cam(clpt, "canonical", 96)
+    renderer.set_meshes_owned(scene)
+    L = clpt.lib()
+    L.CLSetObjects(None, 0)
+    spheres = np.zeros(48, dtype=np.uint8)  # two 24-byte Objects
+    L.CLSetObjects(spheres.ctypes.data, spheres.nbytes)
+    empty_models = L.new_list(0)
+    L.CLSetMeshes(empty_models)  # empty vector: no-op (src/CLState.c:126-129)
+    L.delete_list(empty_models)
+    renderer.set_camera_matrix(cam)
+    renderer.set_params(mode=0, depth=2)
+    renderer.create_image(128, 96)
+    renderer.execute()
+    ref = oracle.render(scene, cam, 128, 96, mode=0, depth=2)
+    _assert_bit_equal(renderer.read_image(), ref["rgba"], "rgba")
+    assert L.CLLastLaunchCount() == 1 and L.CLLastKernelMs() > 0
+
+
+def test_zero_matrix_and_far_camera(clpt, renderer, scene_cache):
+    """Frame 0 of the reference runs with an unset matrix; a camera that misses the
+    scene is all white (src/kernel.cl:421)."""
+    scene, _ = scene_cache("hf22")
+    renderer.set_meshes(scene)
+    renderer.set_params(mode=1, depth=2)
+    renderer.create_image(64, 48)
+    renderer.set_camera_matrix(np.zeros((4, 4), dtype=np.float32))
+    renderer.execute()
+    assert np.isfinite(renderer.read_image()[..., 3]).all()
+    cam = clpt.cam_matrix(clpt.make_camera(position=(0, 50, 0), forward=(0, 1, 0)), 48)
+    renderer.set_camera_matrix(cam)
+    renderer.execute()
+    assert np.array_equal(renderer.read_image(), np.ones((48, 64, 4), dtype=np.float32))
+
+
+def test_full_size_properties_1m(clpt, oracle, renderer):
+    """BASELINE's full size (1080p, ~1M triangles, deep tree): oracle parity on a
+    band of rows, plus size-independent properties over the whole frame."""
+    from clpathtracer_b200 import scenes
+
+    v, c, n = scenes.heightfield(707, False)
+    scene = clpt.build_kd(v, c, n, depth=22)
+    w, h = 1920, 1080
+    cam = _cam(clpt, "canonical", h)
+    img, prim, t, uv = _render_gpu(renderer, scene, cam, w, h, mode=1, depth=2)
+    band = (520, 552)
+    ref = oracle.render(scene, cam, w, h, mode=1, depth=2, rows=band)
+    sl = slice(*band)
+    assert np.array_equal(prim[sl], ref["prim"][sl])
+    _assert_bit_equal(t[sl], ref["t"][sl], "t")
+    _assert_bit_equal(img[sl], ref["rgba"][sl], "rgba")
+    # idempotence
+    img2 = _render_gpu(renderer, scene, cam, w, h, mode=1, depth=2)[0]
+    assert np.array_equal(img, img2)
+    # every reported hit is a real intersection of that triangle at that t (recomputed in float64)
+    ys, xs = np.nonzero(prim >= 0)
+    pick = np.random.default_rng(0).choice(len(ys), 5000, replace=False)
+    ys, xs = ys[pick], xs[pick]
+    tri = scene.tris[:, 0].reshape(-1, 3)[prim[ys, xs]]
+    p0, p1, p2 = (scene.verts[tri[:, k], :3].astype(np.float64) for k in range(3))
+    bary = uv[ys, xs].astype(np.float64)
+    hit = p0 + bary[:, :1] * (p1 - p0) + bary[:, 1:] * (p2 - p0)
+    eye = (cam[:3, 2] / cam[3, 2]).astype(np.float64)
+    dist = np.linalg.norm(hit - eye, axis=1)
+    assert np.allclose(dist, t[ys, xs], rtol=1e-4, atol=1e-5)
+    # depth-1 mirror of a depth-2 frame: mode A and mode B agree on which pixels hit
+    a_img, a_prim, _, _ = _render_gpu(renderer, scene, cam, w, h, mode=0, depth=2)
+    assert np.array_equal(a_prim, prim)
+    assert np.array_equal(a_img[prim < 0], np.ones_like(a_img[prim < 0]))
+
+
+def test_fails_loudly(clpt):
+    """Misuse aborts with a message, like the reference's HANDLE_ERR (src/error.c:147-154)."""
+    root = Path(__file__).resolve().parents[1]
+    code = ("import sys;sys.path.insert(0,%r);import clpathtracer_b200 as cl;L=cl.lib();%s")
+    for body, needle in [("L.CLExecute(64,64)", "CLInit has not been called"),
+                         ("L.CLInit(None,None);L.CLExecute(64,64)", "no render target"),
+                         ("L.CLInit(None,None);L.CLCreateImageHeadless(8,8);L.CLExecute(8,8)", "no scene"),
+                         ("L.CLInit(None,None);L.CLCreateImage(3)", "no OpenGL interop"),
+                         ("L.CLInit(b'k.cl',b'trace')", "no kernel named")]:
+        p = subprocess.run([sys.executable, "-c", code % (str(root), body)], capture_output=True, text=True)
+        assert p.returncode == 1, (body, p.returncode, p.stderr)
+        assert needle in p.stderr, (body, p.stderr)
