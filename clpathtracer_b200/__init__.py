@@ -20,7 +20,8 @@ from pathlib import Path
 import numpy as np
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libclpt.so"
+# $CLPT_LIB selects another build of the same library (kernel experiments)
+LIB_PATH = Path(os.environ["CLPT_LIB"]) if os.environ.get("CLPT_LIB") else PKG / "libclpt.so"
 
 # ---------------------------------------------------------------- wire types
 KDNODE_DTYPE = np.dtype(

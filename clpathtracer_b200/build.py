@@ -48,7 +48,15 @@ def _stale(out: Path, deps: list[Path]) -> bool:
     return any(d.stat().st_mtime > t for d in deps if d.exists())
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, defines: list[str] | None = None,
+          tag: str | None = None) -> Path:
+    """Build libclpt.so; with `tag`, build an experimental variant libclpt_<tag>.so
+    with extra -D defines (selected at run time with $CLPT_LIB)."""
+    global OBJ, LIB
+    if tag:
+        OBJ = PKG / f"_build_{tag}"
+        LIB = PKG / f"libclpt_{tag}.so"
+    defines = ["-D" + d for d in (defines or [])]
     OBJ.mkdir(exist_ok=True)
     inc = ["-I" + str(ROOT / "include"), "-I" + str(CSRC / "cuda")]
     headers = list((ROOT / "include").glob("*.h")) + list((CSRC / "cuda").glob("*.h")) + \
@@ -71,7 +79,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         src, out = CSRC / rel, OBJ / (Path(rel).stem + ".o")
         if force or _stale(out, [src] + headers):
             cmd = [nvcc, *ARCH, "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v",
-                   *inc, "-c", str(src), "-o", str(out)]
+                   *defines, *inc, "-c", str(src), "-o", str(out)]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode != 0:
                 sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
@@ -94,5 +102,9 @@ def build_oracle() -> None:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
-    build_oracle()
+    if "--tag" in sys.argv:
+        t = sys.argv[sys.argv.index("--tag") + 1]
+        print(build(force=True, verbose="-v" in sys.argv, defines=[a[2:] for a in sys.argv if a.startswith("-D")], tag=t))
+    else:
+        print(build(force="--force" in sys.argv, verbose=True))
+        build_oracle()

@@ -20,8 +20,10 @@ CANONICAL_CAMERA = dict(near=0.1, far=1.0, fov=np.pi / 3, position=(0.0, 0.9, -1
 # Default camera of the reference application (src/game.c:275-277).
 REFERENCE_CAMERA = dict(near=0.1, far=1.0, fov=np.pi / 3, position=(0.0, 0.1, -0.2),
                         forward=(0.0, 0.0, 1.0))
-CORNELL_CAMERA = dict(near=0.1, far=1.0, fov=np.pi / 3, position=(0.0, 0.0, -2.6),
-                      forward=(0.0, 0.0, 1.0))
+# Slightly off-axis on purpose: a centred camera sends pixel rays exactly through
+# the mesh edges of the axis-aligned walls (exact u/v ties between neighbours).
+CORNELL_CAMERA = dict(near=0.1, far=1.0, fov=np.pi / 3, position=(0.031, 0.047, -2.6),
+                      forward=(-0.012, -0.018, 0.99976599))
 
 
 def _six_decimals(a: np.ndarray) -> np.ndarray:

@@ -4,7 +4,8 @@
  * device code (src/kernel.cl) is OpenCL C that is JIT-compiled at run time by
  * clBuildProgram (src/CLHandler.c:233-240); there is no OpenCL in the build
  * container, but the GPU box's driver ships libnvidia-opencl.so.1.  This file
- * drives the UNMODIFIED kernel source through it, headless: the GL texture of
+ * drives the reference's kernel source through it (unmodified where the
+ * compiler accepts it; see the build attempts in refcl_render), headless: the GL texture of
  * the reference (src/CLState.c:47-58) is replaced by a plain RGBA/float
  * image2d_t, everything else -- the nine kernel arguments, their order, the
  * raw 68-byte node array and index buffers, NDRange {w,h} with a NULL local
