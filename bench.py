@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--spp", type=int, default=64)
     ap.add_argument("--depth", type=int, default=5, help="bounces + 1")
     ap.add_argument("--grid", type=int, default=707, help="heightfield cells per side (707 -> 999,698 triangles)")
-    ap.add_argument("--tree-depth", type=int, default=int(os.environ.get("CLPT_TREE_DEPTH", "24")))
+    ap.add_argument("--tree-depth", type=int, default=int(os.environ.get("CLPT_TREE_DEPTH", "22")))
     ap.add_argument("--tile-rows", type=int, default=8)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -21,6 +21,16 @@
 // -ffp-contract=off.  Division and square root are the IEEE-rounded ones.
 #include "clpt_device.cuh"
 
+#ifndef CLPT_MIN_BLOCKS
+#define CLPT_MIN_BLOCKS 8 // resident 256-thread blocks per SM the register allocation aims for (measured: 3 -> 2029, 4 -> 2488, 6 -> 2921, 8 -> 3054 Mrays/s)
+#endif
+#ifndef CLPT_PREFETCH_ROPE
+#define CLPT_PREFETCH_ROPE 1
+#endif
+#ifndef CLPT_BRANCHLESS_TRI
+#define CLPT_BRANCHLESS_TRI 0
+#endif
+
 namespace {
 
 struct V3 {
@@ -50,11 +60,17 @@ __device__ __forceinline__ V3 vnormalize(V3 a) {
 }
 __device__ __forceinline__ V3 xyz(float4 a) { return mk(a.x, a.y, a.z); }
 
+// What survives the traversal loop is only the winning triangle SLOT and its t:
+// primitive id, u and v are re-derived afterwards (hit_details) by the same
+// arithmetic on the same operands, which keeps the loop's register footprint low.
 struct Hit {
-    int did_hit;
+    int ref; // triangle slot of the accepted hit, -1 = none
+    float t;
+};
+
+struct HitDetails {
     int prim;
-    int ref; // triangle slot of the accepted hit
-    float t, u, v;
+    float u, v;
 };
 
 struct Counters {
@@ -66,12 +82,8 @@ template <bool COUNT>
 __device__ __forceinline__ Hit closest_hit(const ClptScene &S, V3 o, V3 d, int max_visits,
                                            Counters &cn) {
     Hit h;
-    h.did_hit = 0;
-    h.prim = -1;
-    h.ref = 0;
+    h.ref = -1;
     h.t = 0.0f;
-    h.u = 0.0f;
-    h.v = 0.0f;
     if (COUNT) cn.rays++;
 
     const V3 inv = mk(frcp(d.x), frcp(d.y), frcp(d.z));
@@ -104,14 +116,15 @@ __device__ __forceinline__ Hit closest_hit(const ClptScene &S, V3 o, V3 d, int m
     const float4 *__restrict__ leaves = S.leaves;
     const float4 *__restrict__ tri = S.tri;
 
+    uint2 n = __ldg(nodes);
     for (;;) {
-        // descend to the leaf containing p1, kernel.cl:325-330
-        uint2 n = __ldg(&nodes[index]);
+        // descend to the leaf containing p1, kernel.cl:325-330 (selects, no branches)
         while ((n.y & 3u) != 3u) {
             const unsigned axis = n.y & 3u;
-            const float p = axis == 0 ? p1.x : (axis == 1 ? p1.y : p1.z);
-            index = (int)(n.y >> 2) + (p > __uint_as_float(n.x) ? 1 : 0);
-            n = __ldg(&nodes[index]);
+            float p = axis == 1u ? p1.y : p1.x;
+            p = axis == 2u ? p1.z : p;
+            index = (int)((n.y >> 2) + (p > __uint_as_float(n.x) ? 1u : 0u));
+            n = __ldg(nodes + index);
             if (COUNT) cn.splits++;
         }
         if (COUNT) cn.leaves++;
@@ -119,36 +132,9 @@ __device__ __forceinline__ Hit closest_hit(const ClptScene &S, V3 o, V3 d, int m
         const float4 lmin = __ldg(L), lmax = __ldg(L + 1);
         const int first = __float_as_int(lmin.w), count = __float_as_int(lmax.w);
 
-        // triangle run of the leaf, kernel.cl:333-368 / 227-255
-        for (int i = first; i < first + count; i++) {
-            const float4 a = __ldg(tri + 3 * (size_t)i);
-            const float4 b = __ldg(tri + 3 * (size_t)i + 1);
-            const float4 c = __ldg(tri + 3 * (size_t)i + 2);
-            if (COUNT) cn.tris++;
-            const V3 e1 = xyz(b), e2 = xyz(c);
-            const V3 pvec = vcross(d, e2);
-            const float det = vdot(e1, pvec);
-            if (det < 0.0f) continue;
-            const float idet = frcp(det);
-            const V3 tvec = vsub(o, xyz(a));
-            const float u = fmul(vdot(tvec, pvec), idet);
-            if (u < 0.0f || u > 1.0f) continue;
-            const V3 qvec = vcross(tvec, e1);
-            const float v = fmul(vdot(d, qvec), idet);
-            if (v < 0.0f || fadd(u, v) > 1.0f) continue;
-            const float t = fmul(vdot(e2, qvec), idet);
-            if (!(t > 0.0f)) continue;
-            if (!h.did_hit || t <= min_hit) { // the later triangle wins ties (:344)
-                h.did_hit = 1;
-                min_hit = t;
-                h.prim = __float_as_int(a.w);
-                h.ref = i;
-                h.u = u;
-                h.v = v;
-            }
-        }
-
-        // leaf slab interval and exit face, kernel.cl:146-174
+        // leaf slab interval and exit face, kernel.cl:146-174.  It depends only on the
+        // leaf box and the ray, so it is evaluated BEFORE the triangle run: three
+        // values stay live across the run instead of the eight of the box.
         int far = sx ? 0 : 1;
         {
             const float nx = sx ? lmax.x : lmin.x, fx = sx ? lmin.x : lmax.x;
@@ -169,36 +155,129 @@ __device__ __forceinline__ Hit closest_hit(const ClptScene &S, V3 o, V3 d, int m
                 far = sz ? 4 : 5;
             }
         }
-        // 0.001 is a double literal in the reference (:381)
-        if (h.did_hit && (double)tmin + 0.001 > (double)min_hit) break;
+#if CLPT_PREFETCH_ROPE
+        // The neighbour across the exit face and its node record are requested now,
+        // so the two dependent loads overlap the triangle run instead of following it.
         index = __ldg(reinterpret_cast<const int *>(L + 2) + far);
+        uint2 n_next = make_uint2(0u, 3u);
+        if (index >= 0) n_next = __ldg(nodes + index);
+#endif
+
+        // triangle run of the leaf, kernel.cl:333-368 / 227-255
+        for (int i = first; i < first + count; i++) {
+            const float4 b = __ldg(tri + 3 * (size_t)i + 1);
+            const float4 c = __ldg(tri + 3 * (size_t)i + 2);
+            if (COUNT) cn.tris++;
+            const V3 e1 = xyz(b), e2 = xyz(c);
+            const V3 pvec = vcross(d, e2);
+            const float det = vdot(e1, pvec);
+#if CLPT_BRANCHLESS_TRI
+            // Straight-line variant: the lanes of a warp rarely agree on which test
+            // rejects, so the warp pays for the whole test anyway; predicating it
+            // removes the divergent branches.  Same comparisons, same order.
+            const float4 a = __ldg(tri + 3 * (size_t)i);
+            const float idet = frcp(det);
+            const V3 tvec = vsub(o, xyz(a));
+            const float u = fmul(vdot(tvec, pvec), idet);
+            const V3 qvec = vcross(tvec, e1);
+            const float v = fmul(vdot(d, qvec), idet);
+            const float t = fmul(vdot(e2, qvec), idet);
+            const bool ok = !(det < 0.0f) && !(u < 0.0f || u > 1.0f) && !(v < 0.0f || fadd(u, v) > 1.0f) &&
+                            (t > 0.0f);
+            if (ok && (h.ref < 0 || t <= min_hit)) {
+                min_hit = t;
+                h.ref = i;
+            }
+#else
+            if (det < 0.0f) continue;
+            const float4 a = __ldg(tri + 3 * (size_t)i);
+            const float idet = frcp(det);
+            const V3 tvec = vsub(o, xyz(a));
+            const float u = fmul(vdot(tvec, pvec), idet);
+            if (u < 0.0f || u > 1.0f) continue;
+            const V3 qvec = vcross(tvec, e1);
+            const float v = fmul(vdot(d, qvec), idet);
+            if (v < 0.0f || fadd(u, v) > 1.0f) continue;
+            const float t = fmul(vdot(e2, qvec), idet);
+            if (!(t > 0.0f)) continue;
+            if (h.ref < 0 || t <= min_hit) { // the later triangle wins ties (:344)
+                min_hit = t;
+                h.ref = i;
+            }
+#endif
+        }
+
+        // 0.001 is a double literal in the reference (:381)
+        if (h.ref >= 0 && (double)tmin + 0.001 > (double)min_hit) break;
+#if !CLPT_PREFETCH_ROPE
+        index = __ldg(reinterpret_cast<const int *>(L + 2) + far);
+#endif
         p1 = vadd(o, vscale(d, tmax));
         if (index == -1) break;
         if (++visits >= max_visits) {
             if (COUNT) cn.capped++;
             break;
         }
+#if CLPT_PREFETCH_ROPE
+        n = n_next;
+#else
+        n = __ldg(nodes + index);
+#endif
     }
     h.t = min_hit;
     return h;
 }
 
+// Primitive id and barycentrics of the accepted hit: hit_triangle's u and v
+// (kernel.cl:243-249) evaluated again for the winning slot.
+__device__ __forceinline__ HitDetails hit_details(const ClptScene &S, const Hit &h, V3 o, V3 d) {
+    HitDetails r;
+    const float4 a = __ldg(S.tri + 3 * (size_t)h.ref);
+    const V3 e1 = xyz(__ldg(S.tri + 3 * (size_t)h.ref + 1));
+    const V3 e2 = xyz(__ldg(S.tri + 3 * (size_t)h.ref + 2));
+    const V3 pvec = vcross(d, e2);
+    const float idet = frcp(vdot(e1, pvec));
+    const V3 tvec = vsub(o, xyz(a));
+    r.prim = __float_as_int(a.w);
+    r.u = fmul(vdot(tvec, pvec), idet);
+    r.v = fmul(vdot(d, vcross(tvec, e1)), idet);
+    return r;
+}
+
 // Shading normal of an accepted hit, kernel.cl:349-365.
 template <bool COUNT>
-__device__ __forceinline__ V3 hit_normal(const ClptScene &S, const Hit &h, Counters &cn) {
-    const int4 c1 = __ldg(S.corners + 3 * (size_t)h.prim);
+__device__ __forceinline__ V3 hit_normal(const ClptScene &S, const Hit &h, V3 o, V3 d, Counters &cn) {
+    const int prim = __float_as_int(__ldg(&S.tri[3 * (size_t)h.ref].w));
+    const int4 c1 = __ldg(S.corners + 3 * (size_t)prim);
     if (c1.y >= 0) {
-        const int4 c2 = __ldg(S.corners + 3 * (size_t)h.prim + 1);
-        const int4 c3 = __ldg(S.corners + 3 * (size_t)h.prim + 2);
+        const HitDetails hd = hit_details(S, h, o, d);
+        const int4 c2 = __ldg(S.corners + 3 * (size_t)prim + 1);
+        const int4 c3 = __ldg(S.corners + 3 * (size_t)prim + 2);
         const V3 n1 = xyz(__ldg(S.norms + c1.y)), n2 = xyz(__ldg(S.norms + c2.y)),
                  n3 = xyz(__ldg(S.norms + c3.y));
-        const float w = fsub(fsub(1.0f, h.u), h.v);
+        const float w = fsub(fsub(1.0f, hd.u), hd.v);
         if (COUNT) cn.shade_vn++;
-        return vnormalize(vadd(vadd(vscale(n1, w), vscale(n2, h.u)), vscale(n3, h.v)));
+        return vnormalize(vadd(vadd(vscale(n1, w), vscale(n2, hd.u)), vscale(n3, hd.v)));
     }
     const V3 e1 = xyz(__ldg(S.tri + 3 * (size_t)h.ref + 1));
     const V3 e2 = xyz(__ldg(S.tri + 3 * (size_t)h.ref + 2));
     return vnormalize(vcross(e1, e2));
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void write_aov(const ClptScene &S, const ClptFrame &F, const Hit &h, V3 o, V3 d,
+                                          int x, int y) {
+    const size_t px = (size_t)y * F.width + x;
+    if (h.ref >= 0) {
+        const HitDetails hd = hit_details(S, h, o, d);
+        F.aov_prim[px] = hd.prim;
+        F.aov_t[px] = h.t;
+        F.aov_uv[px] = make_float2(hd.u, hd.v);
+    } else {
+        F.aov_prim[px] = -1;
+        F.aov_t[px] = 0.0f;
+        F.aov_uv[px] = make_float2(0.0f, 0.0f);
+    }
 }
 
 // Philox4x32-10, counter (pixel, sample, dimension block, lane), key (seed, 'clpt').
@@ -275,7 +354,7 @@ __host__ __device__ inline void warp_tile_dims(int log2_ppw, int &tw, int &th) {
 
 template <int MODE, bool COUNT>
 __device__ __forceinline__ V3 trace_sample(const ClptScene &S, const ClptFrame &F, int x, int y, unsigned pixel,
-                                           unsigned sample, bool write_aov, Counters &cn) {
+                                           unsigned sample, bool aov, Counters &cn) {
     const float *M = F.cam;
     const V3 origin = mk(fdiv(M[2], M[14]), fdiv(M[6], M[14]), fdiv(M[10], M[14])); // :443-445
     float fx = fsub((float)(unsigned)x, fdiv((float)(unsigned)F.width, 2.0f));
@@ -294,21 +373,16 @@ __device__ __forceinline__ V3 trace_sample(const ClptScene &S, const ClptFrame &
         V3 Lsum = mk(0.0f, 0.0f, 0.0f), T = mk(1.0f, 1.0f, 1.0f);
         for (int seg = 0; seg < F.depth; seg++) {
             const Hit h = closest_hit<COUNT>(S, o, d, F.max_leaf_visits, cn);
-            if (seg == 0 && write_aov) {
-                const size_t px = (size_t)y * F.width + x;
-                F.aov_prim[px] = h.did_hit ? h.prim : -1;
-                F.aov_t[px] = h.did_hit ? h.t : 0.0f;
-                F.aov_uv[px] = make_float2(h.u, h.v);
-            }
-            if (!h.did_hit) {
+            if (seg == 0 && aov) write_aov<COUNT>(S, F, h, o, d, x, y);
+            if (h.ref < 0) {
                 Lsum = vadd(Lsum, T);
                 break;
             }
-            const V3 nrm = hit_normal<COUNT>(S, h, cn);
+            const V3 nrm = hit_normal<COUNT>(S, h, o, d, cn);
             float al[3] = { 0.5f, 0.5f, 0.5f }, em[3] = { 0.0f, 0.0f, 0.0f };
             int kind = 0;
             if (S.n_materials > 0) {
-                int m = S.tri_material ? __ldg(S.tri_material + h.prim) : 0;
+                int m = S.tri_material ? __ldg(S.tri_material + __float_as_int(__ldg(&S.tri[3 * (size_t)h.ref].w))) : 0;
                 if (m < 0 || m >= S.n_materials) m = 0;
                 const ClptMaterial *mp = S.materials + m;
                 al[0] = mp->albedo[0]; al[1] = mp->albedo[1]; al[2] = mp->albedo[2];
@@ -337,14 +411,9 @@ __device__ __forceinline__ V3 trace_sample(const ClptScene &S, const ClptFrame &
     const int first_depth = depth;
     for (; depth > 0; depth--) {
         const Hit h = closest_hit<COUNT>(S, o, d, F.max_leaf_visits, cn);
-        if (depth == first_depth && write_aov) {
-            const size_t px = (size_t)y * F.width + x;
-            F.aov_prim[px] = h.did_hit ? h.prim : -1;
-            F.aov_t[px] = h.did_hit ? h.t : 0.0f;
-            F.aov_uv[px] = make_float2(h.u, h.v);
-        }
-        if (!h.did_hit) break;
-        const V3 nrm = hit_normal<COUNT>(S, h, cn);
+        if (depth == first_depth && aov) write_aov<COUNT>(S, F, h, o, d, x, y);
+        if (h.ref < 0) break;
+        const V3 nrm = hit_normal<COUNT>(S, h, o, d, cn);
         const V3 nc = mk(fdiv(fadd(nrm.x, 1.0f), 2.0f), fdiv(fadd(nrm.y, 1.0f), 2.0f),
                          fdiv(fadd(nrm.z, 1.0f), 2.0f));
         if (MODE == 0) return nc; // the `return` at :396
@@ -361,7 +430,7 @@ __device__ __forceinline__ V3 trace_sample(const ClptScene &S, const ClptFrame &
 }
 
 template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, CLPT_MIN_BLOCKS)
 render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptFrame F) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int log2_s = F.log2_sample_lanes, s_lanes = 1 << log2_s;
