@@ -47,6 +47,11 @@ def parse_args():
     ap.add_argument("--depth", type=int, default=5, help="bounces + 1")
     ap.add_argument("--grid", type=int, default=707, help="heightfield cells per side (707 -> 999,698 triangles)")
     ap.add_argument("--tree-depth", type=int, default=int(os.environ.get("CLPT_TREE_DEPTH", "22")))
+    ap.add_argument("--builder", default=os.environ.get("CLPT_BUILDER", "sah"), choices=["ref", "sah"],
+                    help="ref: the reference's heuristic at --tree-depth; sah: build_kd_sah (extension)")
+    ap.add_argument("--sah-ci", type=float, default=1.0)
+    ap.add_argument("--sah-bonus", type=float, default=0.9)
+    ap.add_argument("--sah-bins", type=int, default=32)
     ap.add_argument("--tile-rows", type=int, default=8)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -57,9 +62,11 @@ def parse_args():
 def workload_config(a):
     return {
         "workload": f"{a.width}x{a.height}, {a.spp} spp jittered, {a.depth - 1} mirror bounces (depth {a.depth}), "
-                    f"heightfield n={a.grid} ({2 * a.grid * a.grid} triangles), kd depth {a.tree_depth}, canonical camera",
+                    f"heightfield n={a.grid} ({2 * a.grid * a.grid} triangles), kd builder {a.builder}, canonical camera",
         "width": a.width, "height": a.height, "spp": a.spp, "depth": a.depth, "triangles": 2 * a.grid * a.grid,
-        "kd_depth": a.tree_depth, "kd_bins": 25, "mode": "mirror (src/kernel.cl:399-417 enabled)",
+        "kd_builder": ("reference heuristic (src/kd_tree.c:95-200) at depth %d, 25 bins" % a.tree_depth) if a.builder == "ref"
+                      else "build_kd_sah ci=%g bonus=%g bins=%d" % (a.sah_ci, a.sah_bonus, a.sah_bins),
+        "mode": "mirror (src/kernel.cl:399-417 enabled)",
         "sharding": f"row tiles of {a.tile_rows} rows, round-robin over ranks, scene replicated, NCCL all-gather",
         "l2": "flushed between timed frames (CLFlushL2, 256 MiB overwrite, outside the timed events)",
     }
@@ -72,7 +79,10 @@ def make_scene(a):
     t0 = time.time()
     v, c, n = scenes.heightfield(a.grid, False)
     t1 = time.time()
-    scene = cl.build_kd(v, c, n, depth=a.tree_depth)
+    if a.builder == "sah":
+        scene = cl.build_kd_sah(v, c, n, nbins=a.sah_bins, intersect_cost=a.sah_ci, empty_bonus=a.sah_bonus)
+    else:
+        scene = cl.build_kd(v, c, n, depth=a.tree_depth)
     t2 = time.time()
     cam = cl.cam_matrix(cl.make_camera(**scenes.CANONICAL_CAMERA), a.height)
     return scene, cam, {"scene_gen_s": round(t1 - t0, 2), "kd_build_s": round(t2 - t1, 2), **scene.stats()}

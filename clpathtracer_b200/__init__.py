@@ -92,6 +92,7 @@ def lib() -> C.CDLL:
         "cam_matrix_ptr": (None, [C.POINTER(Camera), i, C.POINTER(Matrix)]),
         "build_kd_ex": (KD, [vp, vp, vp, C.c_char_p, i, i]),
         "build_kd": (KD, [vp, vp, vp, C.c_char_p]),
+        "build_kd_sah": (KD, [vp, vp, vp, C.c_char_p, i, i, f, f, f]),
         "parse_kd": (i, [C.c_char_p, C.POINTER(KD)]),
         "write_kd": (i, [C.c_char_p, C.POINTER(KD)]),
         "delete_kd": (None, [KD]),
@@ -213,6 +214,21 @@ def build_kd(verts: np.ndarray, corners: np.ndarray, norms: np.ndarray | None = 
     n4 = _as_vec4(norms) if norms is not None and len(norms) else None
     k = L.build_kd_ex(to_list(np.ascontiguousarray(corners, dtype=np.int32)), to_list(v4), to_list(n4),
                       path.encode() if path else None, depth, nbins)
+    return Scene.from_kd(k)
+
+
+def build_kd_sah(verts: np.ndarray, corners: np.ndarray, norms: np.ndarray | None = None,
+                 max_depth: int | None = None, nbins: int = 32, traversal_cost: float = 1.0,
+                 intersect_cost: float = 1.5, empty_bonus: float = 0.8, path: str | None = None) -> Scene:
+    """SAH kd-tree (extension, clpt_host.h build_kd_sah): same wire format and ropes."""
+    L = lib()
+    v4 = _as_vec4(verts)
+    n4 = _as_vec4(norms) if norms is not None and len(norms) else None
+    if max_depth is None:
+        max_depth = int(8 + 1.3 * np.log2(max(len(corners) // 3, 2)))
+    k = L.build_kd_sah(to_list(np.ascontiguousarray(corners, dtype=np.int32)), to_list(v4), to_list(n4),
+                       path.encode() if path else None, max_depth, nbins, traversal_cost, intersect_cost,
+                       empty_bonus)
     return Scene.from_kd(k)
 
 

@@ -263,6 +263,193 @@ build_cell(tri_set s, const float *bmin, const float *bmax, int depth,
     return out;
 }
 
+
+/* ------------------------------------------------------------------ SAH build
+ * An ADDITION with no counterpart in the reference:
+ * the reference heuristic has no leaf-cost term and a hard depth cap, which at
+ * 1M triangles leaves either ~56 triangles per leaf (depth 15) or millions of
+ * thin and empty cells (deep).  build_kd_sah uses the standard surface-area
+ * heuristic
+ *     cost(plane) = Ct + Ci * (SA(L) * NL + SA(R) * NR) / SA(cell)
+ * (x empty_bonus when one side is empty), makes a leaf when no plane beats
+ * Ci * N, and evaluates candidate planes either on a uniform grid of `nbins`
+ * planes per axis (cells with more than SAH_EXACT_BELOW triangles, O(n + bins)
+ * with histograms) or at every triangle bound inside the cell (small cells).
+ * Triangle bounds are clipped to the cell as they are handed down.  The
+ * preorder wire format and the ropes are the same as above, so the output is
+ * consumed by the same traversal.
+ */
+#define SAH_EXACT_BELOW 48
+
+typedef struct sah_params {
+    int max_depth, nbins;
+    float ct, ci, empty_bonus;
+} sah_params;
+
+static inline float
+box_area(const float *e) {
+    return 2.0f * (e[0] * e[1] + e[1] * e[2] + e[2] * e[0]);
+}
+
+static inline float
+sah_cost(const sah_params *P, const float *ext, int axis, float bmin_a, float v, int NL, int NR, float inv_area) {
+    float el[3] = { ext[0], ext[1], ext[2] }, er[3] = { ext[0], ext[1], ext[2] };
+    el[axis] = v - bmin_a;
+    er[axis] = ext[axis] - el[axis];
+    float c = P->ct + P->ci * (box_area(el) * (float)NL + box_area(er) * (float)NR) * inv_area;
+    if (NL == 0 || NR == 0) {
+        c *= P->empty_bonus;
+    }
+    return c;
+}
+
+static bnode *
+build_cell_sah(tri_set s, const float *bmin, const float *bmax, int depth, const sah_params *P) {
+    bnode *out;
+    if (s.n == 0 || depth == 0) {
+        out = make_leaf(bmin, bmax, &s);
+        tri_set_free(&s);
+        return out;
+    }
+    float ext[3];
+    for (int a = 0; a < 3; a++) {
+        ext[a] = bmax[a] - bmin[a];
+    }
+    const float area = box_area(ext);
+    const float inv_area = area > 0 ? 1.0f / area : 0.0f;
+    const float leaf_cost = P->ci * (float)s.n;
+    float best_cost = leaf_cost;
+    int best_axis = -1;
+    float best_v = 0;
+    const int n = s.n;
+
+    for (int axis = 0; axis < 3 && inv_area > 0; axis++) {
+        if (ext[axis] < KD_EPS) {
+            continue;
+        }
+        const float *lo = s.lo[axis], *hi = s.hi[axis];
+        if (n > SAH_EXACT_BELOW) {
+            /* uniform planes v_i = min + (i+1)/(K+1) * extent; histogram of the
+             * first plane each triangle is "left of" and the last it is "right of" */
+            const int K = P->nbins;
+            float *v = xmalloc(sizeof(float) * (size_t)K);
+            int *hl = calloc((size_t)K + 1, sizeof(int)), *hr = calloc((size_t)K + 1, sizeof(int));
+            if (!hl || !hr) {
+                perror("calloc");
+                exit(EXIT_FAILURE);
+            }
+            for (int i = 0; i < K; i++) {
+                v[i] = bmin[axis] + ((float)(i + 1) / (float)(K + 1)) * ext[axis];
+            }
+            const float scale = (float)(K + 1) / ext[axis];
+            for (int t = 0; t < n; t++) {
+                /* il = smallest i with GOES_LEFT(t, v_i) (K if none); a triangle flat
+                 * on this axis (lo == hi) sits left of a plane through it */
+                const int flat = lo[t] == hi[t];
+                int il = (int)((lo[t] - bmin[axis]) * scale) - 1;
+                il = il < 0 ? 0 : (il > K ? K : il);
+                while (il > 0 && (lo[t] < v[il - 1] || (flat && lo[t] == v[il - 1]))) il--;
+                while (il < K && !(lo[t] < v[il] || (flat && lo[t] == v[il]))) il++;
+                hl[il]++;
+                /* ir = largest i with hi > v_i (-1 if none), stored shifted by one */
+                int ir = (int)((hi[t] - bmin[axis]) * scale) - 1;
+                ir = ir < -1 ? -1 : (ir > K - 1 ? K - 1 : ir);
+                while (ir < K - 1 && hi[t] > v[ir + 1]) ir++;
+                while (ir >= 0 && !(hi[t] > v[ir])) ir--;
+                hr[ir + 1]++;
+            }
+            int NL = 0, NR = n - hr[0];
+            for (int i = 0; i < K; i++) {
+                NL += hl[i];
+                /* NR(i) = triangles whose last right-plane is >= i */
+                if (v[i] > bmin[axis] && v[i] < bmax[axis]) {
+                    float c = sah_cost(P, ext, axis, bmin[axis], v[i], NL, NR, inv_area);
+                    if (c < best_cost) {
+                        best_cost = c;
+                        best_axis = axis;
+                        best_v = v[i];
+                    }
+                }
+                NR -= hr[i + 1];
+            }
+            free(v);
+            free(hl);
+            free(hr);
+        } else {
+            /* every triangle bound strictly inside the cell is a candidate */
+            for (int k = 0; k < 2 * n; k++) {
+                float v = k < n ? lo[k] : hi[k - n];
+                if (!(v > bmin[axis] && v < bmax[axis])) {
+                    continue;
+                }
+                int NL = 0, NR = 0;
+                for (int t = 0; t < n; t++) {
+                    NL += lo[t] < v || (lo[t] == hi[t] && lo[t] == v);
+                    NR += hi[t] > v;
+                }
+                float c = sah_cost(P, ext, axis, bmin[axis], v, NL, NR, inv_area);
+                if (c < best_cost) {
+                    best_cost = c;
+                    best_axis = axis;
+                    best_v = v;
+                }
+            }
+        }
+    }
+    if (best_axis < 0) {
+        out = make_leaf(bmin, bmax, &s);
+        tri_set_free(&s);
+        return out;
+    }
+    /* Partition.  Unlike the reference rule (both sides within 1e-9 of the plane),
+     * a triangle that only TOUCHES the plane stays on its own side, and one lying
+     * in the plane goes left: on meshes whose vertices sit on the candidate planes
+     * the reference rule duplicates every triangle adjacent to a plane. */
+    tri_set L = tri_set_alloc(n), R = tri_set_alloc(n);
+    const float *lo = s.lo[best_axis], *hi = s.hi[best_axis];
+    for (int t = 0; t < n; t++) {
+        if (lo[t] < best_v || (lo[t] == hi[t] && lo[t] == best_v)) {
+            tri_set_push(&L, &s, t);
+            /* clip the handed-down bound to the child */
+            if (L.hi[best_axis][L.n - 1] > best_v) L.hi[best_axis][L.n - 1] = best_v;
+        }
+        if (hi[t] > best_v) {
+            tri_set_push(&R, &s, t);
+            if (R.lo[best_axis][R.n - 1] < best_v) R.lo[best_axis][R.n - 1] = best_v;
+        }
+    }
+    /* a split that separates nothing and removes no volume would recurse forever */
+    if (L.n == n && R.n == n) {
+        tri_set_free(&L);
+        tri_set_free(&R);
+        out = make_leaf(bmin, bmax, &s);
+        tri_set_free(&s);
+        return out;
+    }
+    int big = n >= 1024;
+    tri_set_free(&s);
+    float lmax[3], rmin[3];
+    memcpy(lmax, bmax, sizeof(lmax));
+    memcpy(rmin, bmin, sizeof(rmin));
+    lmax[best_axis] = rmin[best_axis] = best_v;
+    out = xmalloc(sizeof(*out));
+    memcpy(out->bmin, bmin, sizeof(out->bmin));
+    memcpy(out->bmax, bmax, sizeof(out->bmax));
+    out->leaf = 0;
+    out->value = best_v;
+    out->axis = best_axis;
+    out->ids = NULL;
+    out->nids = 0;
+    bnode *kl = NULL, *kr = NULL;
+#pragma omp task shared(kl) firstprivate(L, depth, P) if (big)
+    kl = build_cell_sah(L, bmin, lmax, depth - 1, P);
+    kr = build_cell_sah(R, rmin, bmax, depth - 1, P);
+#pragma omp taskwait
+    out->kid[0] = kl;
+    out->kid[1] = kr;
+    return out;
+}
+
 static void
 count_tree(const bnode *b, size_t *nodes, size_t *refs) {
     /* iterative would need a stack of `depth`; recursion depth <= tree depth */
@@ -464,9 +651,9 @@ kd_get_stats(const kd *tree, kd_stats *out) {
     }
 }
 
-kd
-build_kd_ex(cl_int3 *tris, Vector3 *verts, Vector3 *norms, const char *path,
-            int depth, int nbins) {
+static kd
+build_tree(cl_int3 *tris, Vector3 *verts, Vector3 *norms, const char *path,
+           int depth, int nbins, const sah_params *sah) {
     size_t ncorners = vector_length(tris);
     size_t ntris = ncorners / 3;
     kd tree = { NULL, NULL, verts, norms, tris };
@@ -504,7 +691,8 @@ build_kd_ex(cl_int3 *tris, Vector3 *verts, Vector3 *norms, const char *path,
     bnode *top = NULL;
 #pragma omp parallel
 #pragma omp single
-    top = build_cell(root, bmin.s, bmax.s, depth, nbins);
+    top = sah ? build_cell_sah(root, bmin.s, bmax.s, sah->max_depth, sah)
+              : build_cell(root, bmin.s, bmax.s, depth, nbins);
 
     size_t nnodes = 0, nrefs = 0;
     count_tree(top, &nnodes, &nrefs);
@@ -526,6 +714,20 @@ build_kd_ex(cl_int3 *tris, Vector3 *verts, Vector3 *norms, const char *path,
         free(kdpath);
     }
     return tree;
+}
+
+kd
+build_kd_ex(cl_int3 *tris, Vector3 *verts, Vector3 *norms, const char *path,
+            int depth, int nbins) {
+    return build_tree(tris, verts, norms, path, depth, nbins, NULL);
+}
+
+kd
+build_kd_sah(cl_int3 *tris, Vector3 *verts, Vector3 *norms, const char *path,
+             int max_depth, int nbins, float traversal_cost, float intersect_cost,
+             float empty_bonus) {
+    sah_params P = { max_depth, nbins, traversal_cost, intersect_cost, empty_bonus };
+    return build_tree(tris, verts, norms, path, 0, 0, &P);
 }
 
 kd

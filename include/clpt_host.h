@@ -98,6 +98,14 @@ void cam_matrix_ptr(const Camera *cam, int height, Matrix *out);
 kd build_kd(cl_int3 *tris, Vector3 *verts, Vector3 *norms, const char *path);
 kd build_kd_ex(cl_int3 *tris, Vector3 *verts, Vector3 *norms, const char *path,
                int depth, int nbins);
+/* Extension (no reference counterpart): standard surface-area heuristic with a
+ * leaf-cost termination, `nbins` uniform planes per axis in large cells and all
+ * triangle bounds in small ones.  Same wire format, same ropes.  Suggested:
+ * max_depth 8 + 1.3*log2(triangles), nbins 32, traversal_cost 1, intersect_cost
+ * 1.5, empty_bonus 0.8. */
+kd build_kd_sah(cl_int3 *tris, Vector3 *verts, Vector3 *norms, const char *path,
+                int max_depth, int nbins, float traversal_cost, float intersect_cost,
+                float empty_bonus);
 int parse_kd(const char *filename, kd *tree);  /* kd_tree.h:55; returns 0 on success, 1 on I/O error */
 int write_kd(const char *filename, const kd *tree); /* the writer half of src/kd_tree.c:239-274 */
 void delete_kd(kd tree);                       /* kd_tree.h:58 */

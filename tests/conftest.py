@@ -41,8 +41,8 @@ def scene_cache(clpt):
 
     cache = {}
 
-    def get(name, depth=15, nbins=25):
-        key = (name, depth, nbins)
+    def get(name, depth=15, nbins=25, sah=False):
+        key = (name, depth, nbins, sah)
         if key in cache:
             return cache[key]
         extras = {}
@@ -58,7 +58,10 @@ def scene_cache(clpt):
             v, c, nn = scenes.soup(int(name[4:]))
         else:
             raise KeyError(name)
-        s = clpt.build_kd(v, c, nn, depth=depth, nbins=nbins)
+        if sah:
+            s = clpt.build_kd_sah(v, c, nn, intersect_cost=1.0, empty_bonus=0.9)
+        else:
+            s = clpt.build_kd(v, c, nn, depth=depth, nbins=nbins)
         cache[key] = (s, extras)
         return cache[key]
 

@@ -74,6 +74,22 @@ def test_deterministic_modes_bit_exact(clpt, oracle, renderer, scene_cache, name
     assert (prim >= 0).mean() > (0.01 if name.startswith('soup') else 0.05)  # the camera sees the scene
 
 
+@pytest.mark.parametrize("name,camera,w,h,mode,depth", [("hf224", "canonical", 480, 270, 1, 5),
+                                                         ("cornell", "cornell", 320, 240, 1, 4),
+                                                         ("soup3000", "cornell", 256, 256, 1, 4),
+                                                         ("hf22n", "reference", 333, 197, 0, 2)])
+def test_sah_trees_bit_exact(clpt, oracle, renderer, scene_cache, name, camera, w, h, mode, depth):
+    """Trees from the SAH builder (extension) go through the same traversal."""
+    scene, _ = scene_cache(name, sah=True)
+    cam = _cam(clpt, camera, h)
+    img, prim, t, uv = _render_gpu(renderer, scene, cam, w, h, mode=mode, depth=depth)
+    ref = oracle.render(scene, cam, w, h, mode=mode, depth=depth)
+    assert np.array_equal(prim, ref["prim"])
+    _assert_bit_equal(t, ref["t"], "t")
+    _assert_bit_equal(uv, ref["uv"], "uv")
+    _assert_bit_equal(img, ref["rgba"], "rgba")
+
+
 @pytest.mark.parametrize("depth_tree", [8, 20, 24])
 def test_other_tree_depths(clpt, oracle, renderer, depth_tree):
     """The traversal is tree-agnostic: shallow and deep trees of the same mesh."""
@@ -249,7 +265,7 @@ def test_full_size_properties_1m(clpt, oracle, renderer):
     from clpathtracer_b200 import scenes
 
     v, c, n = scenes.heightfield(707, False)
-    scene = clpt.build_kd(v, c, n, depth=22)
+    scene = clpt.build_kd_sah(v, c, n, intersect_cost=1.0, empty_bonus=0.9)  # the bench tree
     w, h = 1920, 1080
     cam = _cam(clpt, "canonical", h)
     img, prim, t, uv = _render_gpu(renderer, scene, cam, w, h, mode=1, depth=2)

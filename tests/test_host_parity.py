@@ -247,11 +247,28 @@ def test_build_kd_ex_invariants(clpt, depth, nbins):
     assert st["leaves"] * 2 - 1 == st["nodes"]
 
 
+@pytest.mark.parametrize("name", ["hf40", "cornell", "soup3000", "hf4n"])
+def test_build_kd_sah_invariants(clpt, name):
+    """The SAH builder (extension) emits the same wire format: preorder nodes,
+    contiguous leaf runs, every triangle referenced, valid ropes."""
+    v, c, n = _scene_inputs(name)
+    s = clpt.build_kd_sah(v, c, n, intersect_cost=1.0, empty_bonus=0.9)
+    _check_tree_invariants(s)
+    st = s.stats()
+    assert st["leaves"] * 2 - 1 == st["nodes"]
+    ref = clpt.build_kd(v, c, n)
+    # it terminates by cost, not only by depth: far fewer references than the reference heuristic on meshes
+    if name == "hf40":
+        assert st["leaf_tri_refs"] < ref.stats()["leaf_tri_refs"]
+        assert st["max_leaf_tris"] <= 16
+
+
 def test_build_kd_thread_independent(clpt):
     """The parallel evaluation order must not change a single byte."""
     code = ("import sys,hashlib;sys.path.insert(0,%r);import clpathtracer_b200 as cl;"
             "from clpathtracer_b200 import scenes;s=cl.build_kd(*scenes.heightfield(150,False),depth=18);"
-            "print(hashlib.sha256(s.nodes.tobytes()+s.tri_indices.tobytes()).hexdigest())") % str(
+            "t=cl.build_kd_sah(*scenes.heightfield(150,False));"
+            "print(hashlib.sha256(s.nodes.tobytes()+s.tri_indices.tobytes()+t.nodes.tobytes()+t.tri_indices.tobytes()).hexdigest())") % str(
                 Path(__file__).resolve().parents[1])
     digests = set()
     for threads in ("1", "3", "8"):

@@ -73,15 +73,17 @@ def _brute_force(scene, cam, w, h):
     return best_t.reshape(h, w), best_id.reshape(h, w)
 
 
-@pytest.mark.parametrize("name,camera", [("hf22", "canonical"), ("cornell", "cornell"), ("soup500", "cornell")])
-def test_traversal_against_brute_force(clpt, oracle, scene_cache, name, camera):
+@pytest.mark.parametrize("name,camera,sah", [("hf22", "canonical", False), ("cornell", "cornell", False),
+                                             ("soup500", "cornell", False), ("hf22", "canonical", True),
+                                             ("cornell", "cornell", True), ("soup500", "cornell", True)])
+def test_traversal_against_brute_force(clpt, oracle, scene_cache, name, camera, sah):
     """Rope traversal must find the globally closest front-facing hit.  The
     reference traversal is not watertight (split-plane
     cracks), so a small classified budget of misses is allowed; where both find a
     hit on the same triangle, t is bit-identical."""
     from clpathtracer_b200 import scenes
 
-    scene, _ = scene_cache(name)
+    scene, _ = scene_cache(name, sah=sah)
     w, h = 96, 72
     kw = {"canonical": scenes.CANONICAL_CAMERA, "cornell": scenes.CORNELL_CAMERA}[camera]
     cam = clpt.cam_matrix(clpt.make_camera(**kw), h)
