@@ -175,16 +175,17 @@ def run_reference(a):
 
     scene, cam, info = make_scene(a)
     cores = op.oracle().oracle_num_threads()
-    kw = dict(mode=1, depth=a.depth, spp=1, flags=op.FLAG_JITTER, aov=False)
+    ref_spp = min(8, a.spp)
+    kw = dict(mode=1, depth=a.depth, spp=ref_spp, flags=op.FLAG_JITTER, aov=False)
     for w in range(a.warmup):
-        op.render(scene, cam, a.width, a.height, seed=a.seed, sample_base=w, **kw)
+        op.render(scene, cam, a.width, a.height, seed=a.seed, sample_base=w * ref_spp, **kw)
     rays, t0 = 0, time.time()
     for k in range(a.steps):
-        rays += op.render(scene, cam, a.width, a.height, seed=a.seed, sample_base=k, **kw)["counters"]["rays"]
+        rays += op.render(scene, cam, a.width, a.height, seed=a.seed, sample_base=k * ref_spp, **kw)["counters"]["rays"]
     secs = time.time() - t0
     value = rays / secs / 1e6
-    sample = f"each step = the full {a.width}x{a.height} frame at 1 of {a.spp} spp, depth {a.depth}"
-    print(json.dumps({
+    sample = f"each step = the full {a.width}x{a.height} frame at {ref_spp} of {a.spp} spp, depth {a.depth}"
+    emit({
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(secs / a.steps * 1e3, 2),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -192,11 +193,33 @@ def run_reference(a):
         "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "scene": info,
-    }))
+    })
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything but the final JSON line goes to stderr (NCCL and friends print
+    banners on stdout): fd 1 is pointed at fd 2 until emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        os.write(1, line)
+    else:
+        os.write(_REAL_STDOUT, line)
 
 
 def main():
     a = parse_args()
+    quiet_stdout()
     if a.impl == "reference":
         return run_reference(a)
 
@@ -335,7 +358,7 @@ def main():
             out["cpu_baseline"] = cpu_baseline(a, scene, cam, a.cpu_seconds)
         else:
             out["cpu_baseline"] = None
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         L.CLDistShutdown()
     r.close()
