@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--sah-ci", type=float, default=1.0)
     ap.add_argument("--sah-bonus", type=float, default=0.9)
     ap.add_argument("--sah-bins", type=int, default=32)
+    ap.add_argument("--engine", type=int, default=int(os.environ.get("CLPT_ENGINE", "0")),
+                    help="0 auto, 1 megakernel, 2 wavefront")
     ap.add_argument("--tile-rows", type=int, default=8)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -246,6 +248,7 @@ def main():
     r = cl.Renderer(device=local)
     r.set_meshes(scene)
     r.set_camera_matrix(cam)
+    L.CLSetEngine(a.engine)
     if world > 1:
         # the NCCL id is made by rank 0 and carried over torch.distributed (plumbing only)
         idbuf = torch.zeros(128, dtype=torch.uint8)
@@ -353,6 +356,7 @@ def main():
             "capped_rays": tot["capped"],
             "ms_per_frame": round(ms_per_step, 4), "wall_ms_per_step_incl_flush": round(wall / a.steps * 1e3, 3),
             "device": L.CLDeviceName().decode(), "scene": info,
+            "engine": {1: "megakernel", 2: "wavefront"}[L.CLLastEngine()],
         }
         if world == 1 and not a.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(a, scene, cam, a.cpu_seconds)

@@ -110,7 +110,7 @@ def lib() -> C.CDLL:
         "CLSetMaterials": (None, [vp, sz, vp, sz]),
         "CLDeleteImage": (None, []), "CLCreateImage": (None, [u]), "CLExecute": (None, [i, i]),
         "CLSelectDevice": (None, [i]), "CLSetRenderParams": (None, [i, i, i, u, i]),
-        "CLSetMaxLeafVisits": (None, [i]), "CLCreateImageHeadless": (None, [i, i]),
+        "CLSetMaxLeafVisits": (None, [i]), "CLSetEngine": (None, [i]), "CLLastEngine": (i, []), "CLCreateImageHeadless": (None, [i, i]),
         "CLResetAccumulation": (None, []), "CLReadImage": (None, [vp, sz]),
         "CLEnableAOV": (None, [i]), "CLReadAOV": (None, [vp, vp, vp]),
         "CLGetCounters": (None, [vp]), "CLLastKernelMs": (f, []), "CLLastLaunchCount": (i, []),

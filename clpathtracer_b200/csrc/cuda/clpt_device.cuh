@@ -70,3 +70,11 @@ void clpt_launch_deinterleave(const float4 *gathered, float4 *image, int width, 
 void clpt_launch_fill(float4 *dst, size_t n, float value, cudaStream_t stream);
 void clpt_launch_normalise(const float4 *src, float4 *dst, size_t n, cudaStream_t stream);
 const void *clpt_render_kernel_symbol(void);
+
+// wavefront.cu: the same frame as clpt_launch_render for modes 0/1, organised as
+// generate / trace / shade / resolve passes over ray queues in `workspace`
+// (clpt_wavefront_workspace_bytes(max_paths) bytes).  Returns the number of
+// kernels launched, or -1 if the workspace cannot hold one image row.
+size_t clpt_wavefront_workspace_bytes(size_t max_paths);
+int clpt_launch_wavefront(const ClptScene &scene, const ClptFrame &frame, void *workspace, size_t max_paths,
+                          int sm_count, cudaStream_t stream);

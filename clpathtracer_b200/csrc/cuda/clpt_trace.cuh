@@ -1,0 +1,355 @@
+// clpt_trace.cuh -- device functions shared by the render kernels (internal).
+//
+// fp32 helpers that are never contracted into FMAs, the per-ray traversal of
+// the packed kd-tree (src/kernel.cl:311-389), hit shading inputs, Philox, and
+// camera ray generation (src/kernel.cl:443-456).  See render_kernel.cu for the
+// numerics contract; every kernel that traces rays includes this file so that
+// there is exactly one statement of the arithmetic.
+#pragma once
+
+#include "clpt_device.cuh"
+
+#ifndef CLPT_MIN_BLOCKS
+#define CLPT_MIN_BLOCKS 8 // resident 256-thread blocks per SM the register allocation aims for (measured: 3 -> 2029, 4 -> 2488, 6 -> 2921, 8 -> 3054 Mrays/s)
+#endif
+
+namespace {
+
+struct V3 {
+    float x, y, z;
+};
+
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+// 1/x: the correctly rounded reciprocal is the same number as the IEEE quotient 1.0f/x
+__device__ __forceinline__ float frcp(float a) { return __frcp_rn(a); }
+__device__ __forceinline__ V3 mk(float x, float y, float z) { V3 r = { x, y, z }; return r; }
+__device__ __forceinline__ V3 vadd(V3 a, V3 b) { return mk(fadd(a.x, b.x), fadd(a.y, b.y), fadd(a.z, b.z)); }
+__device__ __forceinline__ V3 vsub(V3 a, V3 b) { return mk(fsub(a.x, b.x), fsub(a.y, b.y), fsub(a.z, b.z)); }
+__device__ __forceinline__ V3 vscale(V3 a, float k) { return mk(fmul(a.x, k), fmul(a.y, k), fmul(a.z, k)); }
+__device__ __forceinline__ float vdot(V3 a, V3 b) {
+    return fadd(fadd(fmul(a.x, b.x), fmul(a.y, b.y)), fmul(a.z, b.z));
+}
+__device__ __forceinline__ V3 vcross(V3 a, V3 b) {
+    return mk(fsub(fmul(a.y, b.z), fmul(a.z, b.y)), fsub(fmul(a.z, b.x), fmul(a.x, b.z)),
+              fsub(fmul(a.x, b.y), fmul(a.y, b.x)));
+}
+__device__ __forceinline__ V3 vnormalize(V3 a) {
+    float len = __fsqrt_rn(vdot(a, a));
+    return mk(fdiv(a.x, len), fdiv(a.y, len), fdiv(a.z, len));
+}
+__device__ __forceinline__ V3 xyz(float4 a) { return mk(a.x, a.y, a.z); }
+
+// What survives the traversal loop is only the winning triangle SLOT and its t:
+// primitive id, u and v are re-derived afterwards (hit_details) by the same
+// arithmetic on the same operands, which keeps the loop's register footprint low.
+struct Hit {
+    int ref; // triangle slot of the accepted hit, -1 = none
+    float t;
+};
+
+struct HitDetails {
+    int prim;
+    float u, v;
+};
+
+struct Counters {
+    unsigned int rays, splits, leaves, tris, shade_vn, capped;
+};
+
+// ---- the four steps of the traversal, src/kernel.cl:311-389 ----------------
+// They are separate functions because two kernels compose them differently: the
+// megakernel runs one ray to completion per call (closest_hit below), the
+// wavefront trace kernel keeps one ray per lane and refills lanes as rays end.
+
+// Root clip, kernel.cl:101-144.  False when the ray misses the scene box.
+__device__ __forceinline__ bool root_clip(const ClptScene &S, V3 o, V3 inv, float &tmin, float &tmax) {
+    const bool sx = inv.x < 0.0f, sy = inv.y < 0.0f, sz = inv.z < 0.0f;
+    const float nx = sx ? S.root_max[0] : S.root_min[0], fx = sx ? S.root_min[0] : S.root_max[0];
+    const float ny = sy ? S.root_max[1] : S.root_min[1], fy = sy ? S.root_min[1] : S.root_max[1];
+    const float nz = sz ? S.root_max[2] : S.root_min[2], fz = sz ? S.root_min[2] : S.root_max[2];
+    tmin = fmul(fsub(nx, o.x), inv.x);
+    tmax = fmul(fsub(fx, o.x), inv.x);
+    const float tymin = fmul(fsub(ny, o.y), inv.y), tymax = fmul(fsub(fy, o.y), inv.y);
+    if ((tmin > tymax) || (tymin > tmax)) return false;
+    if (tymin > tmin) tmin = tymin;
+    if (tymax < tmax) tmax = tymax;
+    const float tzmin = fmul(fsub(nz, o.z), inv.z), tzmax = fmul(fsub(fz, o.z), inv.z);
+    if ((tmin > tzmax) || (tzmin > tmax)) return false;
+    if (tzmin > tmin) tmin = tzmin;
+    if (tzmax < tmax) tmax = tzmax;
+    return tmax > 0.0f;
+}
+
+// Descend from node word n to the leaf containing p1, kernel.cl:325-330
+// (selects, no branches).  Returns the leaf's node word.
+template <bool COUNT>
+__device__ __forceinline__ uint2 descend(const uint2 *__restrict__ nodes, uint2 n, V3 p1, Counters &cn) {
+    while ((n.y & 3u) != 3u) {
+        const unsigned axis = n.y & 3u;
+        float p = axis == 1u ? p1.y : p1.x;
+        p = axis == 2u ? p1.z : p;
+        const unsigned index = (n.y >> 2) + (p > __uint_as_float(n.x) ? 1u : 0u);
+        n = __ldg(nodes + index);
+        if (COUNT) cn.splits++;
+    }
+    return n;
+}
+
+// Leaf slab interval and exit face, kernel.cl:146-174.
+__device__ __forceinline__ void leaf_interval(float4 lmin, float4 lmax, V3 o, V3 inv, float &tmin, float &tmax,
+                                              int &far) {
+    const bool sx = inv.x < 0.0f, sy = inv.y < 0.0f, sz = inv.z < 0.0f;
+    far = sx ? 0 : 1;
+    const float nx = sx ? lmax.x : lmin.x, fx = sx ? lmin.x : lmax.x;
+    const float ny = sy ? lmax.y : lmin.y, fy = sy ? lmin.y : lmax.y;
+    const float nz = sz ? lmax.z : lmin.z, fz = sz ? lmin.z : lmax.z;
+    tmin = fmul(fsub(nx, o.x), inv.x);
+    tmax = fmul(fsub(fx, o.x), inv.x);
+    const float tymin = fmul(fsub(ny, o.y), inv.y), tymax = fmul(fsub(fy, o.y), inv.y);
+    if (tymin > tmin) tmin = tymin;
+    if (tymax < tmax) {
+        tmax = tymax;
+        far = sy ? 2 : 3;
+    }
+    const float tzmin = fmul(fsub(nz, o.z), inv.z), tzmax = fmul(fsub(fz, o.z), inv.z);
+    if (tzmin > tmin) tmin = tzmin;
+    if (tzmax < tmax) {
+        tmax = tzmax;
+        far = sz ? 4 : 5;
+    }
+}
+
+// Triangle run of a leaf, kernel.cl:333-368 / 227-255.  Early exits are kept as
+// branches: a fully predicated test measured 8% slower (profiles/).
+template <bool COUNT>
+__device__ __forceinline__ void triangle_run(const float4 *__restrict__ tri, int first, int count, V3 o, V3 d,
+                                             int &ref, float &min_hit, Counters &cn) {
+    for (int i = first; i < first + count; i++) {
+        const float4 b = __ldg(tri + 3 * (size_t)i + 1);
+        const float4 c = __ldg(tri + 3 * (size_t)i + 2);
+        if (COUNT) cn.tris++;
+        const V3 e1 = xyz(b), e2 = xyz(c);
+        const V3 pvec = vcross(d, e2);
+        const float det = vdot(e1, pvec);
+        if (det < 0.0f) continue;
+        const float4 a = __ldg(tri + 3 * (size_t)i);
+        const float idet = frcp(det);
+        const V3 tvec = vsub(o, xyz(a));
+        const float u = fmul(vdot(tvec, pvec), idet);
+        if (u < 0.0f || u > 1.0f) continue;
+        const V3 qvec = vcross(tvec, e1);
+        const float v = fmul(vdot(d, qvec), idet);
+        if (v < 0.0f || fadd(u, v) > 1.0f) continue;
+        const float t = fmul(vdot(e2, qvec), idet);
+        if (!(t > 0.0f)) continue;
+        if (ref < 0 || t <= min_hit) { // the later triangle wins ties (:344)
+            min_hit = t;
+            ref = i;
+        }
+    }
+}
+
+// Early-out after a leaf: 0.001 is a double literal in the reference (:381).
+__device__ __forceinline__ bool hit_is_final(int ref, float tmin, float min_hit) {
+    return ref >= 0 && (double)tmin + 0.001 > (double)min_hit;
+}
+
+// Traversal of one ray to completion.
+template <bool COUNT>
+__device__ __forceinline__ Hit closest_hit(const ClptScene &S, V3 o, V3 d, int max_visits,
+                                           Counters &cn) {
+    Hit h;
+    h.ref = -1;
+    h.t = 0.0f;
+    if (COUNT) cn.rays++;
+    const V3 inv = mk(frcp(d.x), frcp(d.y), frcp(d.z));
+    float tmin, tmax;
+    if (!root_clip(S, o, inv, tmin, tmax)) return h;
+    V3 p1 = o;
+    if (tmin > 0.0f) p1 = vadd(p1, vscale(d, tmin));
+
+    int visits = 0;
+    float min_hit = 0.0f;
+    const uint2 *__restrict__ nodes = S.nodes;
+    uint2 n = __ldg(nodes);
+    for (;;) {
+        n = descend<COUNT>(nodes, n, p1, cn);
+        if (COUNT) cn.leaves++;
+        const float4 *L = S.leaves + 4 * (size_t)n.x;
+        const float4 lmin = __ldg(L), lmax = __ldg(L + 1);
+        // The exit depends only on the leaf box and the ray, so it is evaluated BEFORE
+        // the triangle run: three values stay live across the run instead of eight.
+        int far;
+        leaf_interval(lmin, lmax, o, inv, tmin, tmax, far);
+        // The neighbour across the exit face and its node word are requested now, so
+        // the two dependent loads overlap the triangle run instead of following it.
+        const int next = __ldg(reinterpret_cast<const int *>(L + 2) + far);
+        uint2 n_next = make_uint2(0u, 3u);
+        if (next >= 0) n_next = __ldg(nodes + next);
+        triangle_run<COUNT>(S.tri, __float_as_int(lmin.w), __float_as_int(lmax.w), o, d, h.ref, min_hit, cn);
+        if (hit_is_final(h.ref, tmin, min_hit)) break;
+        p1 = vadd(o, vscale(d, tmax)); // :385
+        if (next == -1) break;
+        if (++visits >= max_visits) {
+            if (COUNT) cn.capped++;
+            break;
+        }
+        n = n_next;
+    }
+    h.t = min_hit;
+    return h;
+}
+
+// Primitive id and barycentrics of the accepted hit: hit_triangle's u and v
+// (kernel.cl:243-249) evaluated again for the winning slot.
+__device__ __forceinline__ HitDetails hit_details(const ClptScene &S, const Hit &h, V3 o, V3 d) {
+    HitDetails r;
+    const float4 a = __ldg(S.tri + 3 * (size_t)h.ref);
+    const V3 e1 = xyz(__ldg(S.tri + 3 * (size_t)h.ref + 1));
+    const V3 e2 = xyz(__ldg(S.tri + 3 * (size_t)h.ref + 2));
+    const V3 pvec = vcross(d, e2);
+    const float idet = frcp(vdot(e1, pvec));
+    const V3 tvec = vsub(o, xyz(a));
+    r.prim = __float_as_int(a.w);
+    r.u = fmul(vdot(tvec, pvec), idet);
+    r.v = fmul(vdot(d, vcross(tvec, e1)), idet);
+    return r;
+}
+
+// Shading normal of an accepted hit, kernel.cl:349-365.
+template <bool COUNT>
+__device__ __forceinline__ V3 hit_normal(const ClptScene &S, const Hit &h, V3 o, V3 d, Counters &cn) {
+    const int prim = __float_as_int(__ldg(&S.tri[3 * (size_t)h.ref].w));
+    const int4 c1 = __ldg(S.corners + 3 * (size_t)prim);
+    if (c1.y >= 0) {
+        const HitDetails hd = hit_details(S, h, o, d);
+        const int4 c2 = __ldg(S.corners + 3 * (size_t)prim + 1);
+        const int4 c3 = __ldg(S.corners + 3 * (size_t)prim + 2);
+        const V3 n1 = xyz(__ldg(S.norms + c1.y)), n2 = xyz(__ldg(S.norms + c2.y)),
+                 n3 = xyz(__ldg(S.norms + c3.y));
+        const float w = fsub(fsub(1.0f, hd.u), hd.v);
+        if (COUNT) cn.shade_vn++;
+        return vnormalize(vadd(vadd(vscale(n1, w), vscale(n2, hd.u)), vscale(n3, hd.v)));
+    }
+    const V3 e1 = xyz(__ldg(S.tri + 3 * (size_t)h.ref + 1));
+    const V3 e2 = xyz(__ldg(S.tri + 3 * (size_t)h.ref + 2));
+    return vnormalize(vcross(e1, e2));
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void write_aov(const ClptScene &S, const ClptFrame &F, const Hit &h, V3 o, V3 d,
+                                          int x, int y) {
+    const size_t px = (size_t)y * F.width + x;
+    if (h.ref >= 0) {
+        const HitDetails hd = hit_details(S, h, o, d);
+        F.aov_prim[px] = hd.prim;
+        F.aov_t[px] = h.t;
+        F.aov_uv[px] = make_float2(hd.u, hd.v);
+    } else {
+        F.aov_prim[px] = -1;
+        F.aov_t[px] = 0.0f;
+        F.aov_uv[px] = make_float2(0.0f, 0.0f);
+    }
+}
+
+// Philox4x32-10, counter (pixel, sample, dimension block, lane), key (seed, 'clpt').
+__device__ __forceinline__ void philox(unsigned c[4], unsigned k0, unsigned k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const unsigned n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0;
+        c[1] = lo1;
+        c[2] = n2;
+        c[3] = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+__device__ __forceinline__ float u01(unsigned x) { return fmul((float)(x >> 8), 0x1p-24f); }
+#define CLPT_KEY1 0x636c7074u
+
+// Cosine-weighted direction about n (extension; oracle_kernel.c cosine_dir).
+__device__ __forceinline__ V3 cosine_dir(V3 n, unsigned pixel, unsigned sample, unsigned bounce,
+                                         unsigned seed) {
+    float a = 0.0f, b = 0.0f;
+    bool found = false;
+#pragma unroll 1
+    for (unsigned blk = 0; blk < 2 && !found; blk++) {
+        unsigned c[4] = { pixel, sample, 1u + bounce, blk };
+        philox(c, seed, CLPT_KEY1);
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const float x = fsub(fmul(2.0f, u01(c[2 * k])), 1.0f);
+            const float y = fsub(fmul(2.0f, u01(c[2 * k + 1])), 1.0f);
+            if (!found && fadd(fmul(x, x), fmul(y, y)) <= 1.0f) {
+                a = x;
+                b = y;
+                found = true;
+            }
+        }
+    }
+    const float zz = fsub(fsub(1.0f, fmul(a, a)), fmul(b, b));
+    const float z = __fsqrt_rn(zz > 0.0f ? zz : 0.0f);
+    const float sg = n.z >= 0.0f ? 1.0f : -1.0f;
+    const float p = fdiv(-1.0f, fadd(sg, n.z));
+    const float q = fmul(fmul(n.x, n.y), p);
+    const V3 t1 = mk(fadd(1.0f, fmul(fmul(fmul(sg, n.x), n.x), p)), fmul(sg, q), fmul(-sg, n.x));
+    const V3 t2 = mk(q, fadd(sg, fmul(fmul(n.y, n.y), p)), -n.y);
+    return vnormalize(vadd(vadd(vscale(t1, a), vscale(t2, b)), vscale(n, z)));
+}
+
+__device__ __forceinline__ V3 unproject(const float *M, V3 X) { // kernel.cl:89-94
+    const float w = fadd(fadd(fadd(fmul(M[12], X.x), fmul(M[13], X.y)), fmul(M[14], X.z)), M[15]);
+    const float a = fadd(fadd(fadd(fmul(M[0], X.x), fmul(M[1], X.y)), fmul(M[2], X.z)), M[3]);
+    const float b = fadd(fadd(fadd(fmul(M[4], X.x), fmul(M[5], X.y)), fmul(M[6], X.z)), M[7]);
+    const float c = fadd(fadd(fadd(fmul(M[8], X.x), fmul(M[9], X.y)), fmul(M[10], X.z)), M[11]);
+    return mk(fdiv(a, w), fdiv(b, w), fdiv(c, w));
+}
+
+
+// Camera ray of one pixel sample, kernel.cl:443-456 (+ optional Philox jitter,
+// dimension block 0).  Without jitter this is exactly the reference's ray.
+__device__ __forceinline__ void primary_ray(const ClptFrame &F, int x, int y, unsigned pixel, unsigned sample,
+                                            V3 &o, V3 &d) {
+    const float *M = F.cam;
+    o = mk(fdiv(M[2], M[14]), fdiv(M[6], M[14]), fdiv(M[10], M[14])); // :443-445
+    float fx = fsub((float)(unsigned)x, fdiv((float)(unsigned)F.width, 2.0f));
+    float fy = fsub((float)(unsigned)y, fdiv((float)(unsigned)F.height, 2.0f));
+    if (F.flags & CLPT_F_JITTER) {
+        unsigned c[4] = { pixel, sample, 0u, 0u };
+        philox(c, F.seed, CLPT_KEY1);
+        fx = fadd(fx, fsub(u01(c[0]), 0.5f));
+        fy = fadd(fy, fsub(u01(c[1]), 0.5f));
+    }
+    const V3 ncp = unproject(M, mk(fx, fy, -1.0f));
+    const V3 fcp = unproject(M, mk(fx, fy, 1.0f));
+    d = vnormalize(vsub(fcp, ncp));
+}
+
+// Row of this rank's slab -> image row: tiles of tile_rows rows dealt round-robin.
+__device__ __forceinline__ int slab_row_to_image_row(const ClptFrame &F, int ly) {
+    const int lt = ly / F.tile_rows;
+    return (lt * F.nranks + F.rank) * F.tile_rows + (ly - lt * F.tile_rows);
+}
+
+// Final store of a pixel's ordered sample sum (shared by both engines).
+__device__ __forceinline__ void store_pixel(const ClptFrame &F, int x, int ly, V3 acc, int spp) {
+    float4 *dst = F.target + (size_t)ly * F.width + x;
+    if (F.flags & CLPT_F_ACCUMULATE) {
+        const float4 prev = *dst;
+        *dst = make_float4(fadd(prev.x, acc.x), fadd(prev.y, acc.y), fadd(prev.z, acc.z),
+                           fadd(prev.w, (float)spp));
+    } else if (spp == 1) {
+        *dst = make_float4(acc.x, acc.y, acc.z, 1.0f);
+    } else {
+        const float k = fdiv(1.0f, (float)spp);
+        *dst = make_float4(fmul(acc.x, k), fmul(acc.y, k), fmul(acc.z, k), 1.0f);
+    }
+}
+
+} // namespace

@@ -135,6 +135,10 @@ struct {
     float last_kernel_ms = 0;
     int last_launches = 0;
     DevBuf<unsigned char> l2_flush;
+    int engine = 0; // 0 auto, 1 megakernel, 2 wavefront
+    int last_engine = 1;
+    DevBuf<unsigned char> wf_workspace;
+    size_t wf_max_paths = 0;
 
     int rank = 0, nranks = 1, tile_rows = 8;
     ncclComm_t comm = nullptr;
@@ -284,10 +288,37 @@ void clpt_state_launch_frame(int width, int height) {
         F.counters = St.counters.ptr;
     }
 
+    // Engine.  Measured on the bench workload (profiles/r01_wavefront_experiment.json)
+    // the megakernel with its sample-lane mapping is faster (57.7 ms against 91.3 ms
+    // for the best wavefront setting), so "automatic" means megakernel; the wavefront
+    // engine stays selectable and is held to the same bit-exact parity tests.
+    bool wavefront = St.engine == 2;
+    if (St.mode == CLPT_MODE_PATH) wavefront = false; // mode C exists in the megakernel only
+    if (wavefront) {
+        const size_t want_paths = (size_t)F.local_rows * width * (size_t)(St.spp < 1 ? 1 : St.spp);
+        size_t cap = 48u << 20; // paths per chunk
+        if (const char *env = getenv("CLPT_WF_MAX_PATHS")) cap = (size_t)atoll(env);
+        const size_t row_paths = (size_t)width * (size_t)(St.spp < 1 ? 1 : St.spp);
+        size_t paths = want_paths < cap ? want_paths : cap;
+        if (paths < row_paths) paths = row_paths;
+        if (St.wf_max_paths != paths) {
+            St.wf_workspace.resize(clpt_wavefront_workspace_bytes(paths));
+            St.wf_max_paths = paths;
+        }
+    }
+    St.last_engine = wavefront ? 2 : 1;
+
     CU(cudaEventRecord(St.ev_start, St.stream));
-    clpt_launch_render(St.scene, F, St.stream);
+    if (wavefront) {
+        const int n = clpt_launch_wavefront(St.scene, F, St.wf_workspace.ptr, St.wf_max_paths,
+                                            St.prop.multiProcessorCount, St.stream);
+        if (n < 0) FATAL("wavefront workspace too small");
+        St.last_launches += n;
+    } else {
+        clpt_launch_render(St.scene, F, St.stream);
+        St.last_launches++;
+    }
     CU(cudaGetLastError());
-    St.last_launches++;
     CU(cudaEventRecord(St.ev_stop, St.stream));
 
     if (St.nranks > 1 && St.comm) {
@@ -374,6 +405,8 @@ void CLTerminate(void) {
     St.aov_uv.release();
     St.counters.release();
     St.l2_flush.release();
+    St.wf_workspace.release();
+    St.wf_max_paths = 0;
     CU(cudaEventDestroy(St.ev_start));
     CU(cudaEventDestroy(St.ev_stop));
     for (auto &e : St.ev_user) CU(cudaEventDestroy(e));
@@ -458,6 +491,13 @@ void CLSetRenderParams(int mode, int depth, int spp, unsigned int seed, int flag
     St.seed = seed;
     St.flags = flags;
 }
+
+void CLSetEngine(int engine) {
+    if (engine < 0 || engine > 2) FATAL("CLSetEngine: 0 auto, 1 megakernel, 2 wavefront");
+    St.engine = engine;
+}
+
+int CLLastEngine(void) { return St.last_engine; }
 
 void CLSetMaxLeafVisits(int cap) {
     if (cap < 1) FATAL("CLSetMaxLeafVisits: cap must be >= 1");

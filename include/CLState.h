@@ -112,6 +112,11 @@ void CLSetMaterials(const CLMaterial *materials, size_t material_bytes,
  * samples per pixel per frame, RNG seed, CLPT_FLAG_* */
 void CLSetRenderParams(int mode, int depth, int spp, unsigned int seed, int flags);
 void CLSetMaxLeafVisits(int cap);          /* rope-hop cap per ray; default 4096 */
+/* Execution engine: 0 = automatic, 1 = megakernel (one thread runs a whole path),
+ * 2 = wavefront (generate / trace / shade / resolve passes over ray queues in HBM).
+ * Both produce the same bits; the choice is about speed only. */
+void CLSetEngine(int engine);
+int CLLastEngine(void);                    /* engine the last CLExecute used: 1 or 2 */
 void CLCreateImageHeadless(int width, int height); /* float4 target, zeroed */
 void CLResetAccumulation(void);            /* zero the target and the sample counter */
 /* Blocking device->host copy of the whole float4 frame (bytes must be

@@ -90,6 +90,72 @@ def test_sah_trees_bit_exact(clpt, oracle, renderer, scene_cache, name, camera, 
     _assert_bit_equal(img, ref["rgba"], "rgba")
 
 
+WF_CASES = [
+    # scene, sah, camera, w, h, mode, depth, spp, flags
+    ("hf22n", False, "canonical", 320, 240, 1, 5, 1, 0),
+    ("hf22", True, "canonical", 333, 197, 1, 3, 6, 1),       # spp not a power of two, jitter
+    ("cornell", True, "cornell", 320, 240, 1, 4, 4, 1),
+    ("soup3000", False, "cornell", 256, 256, 1, 4, 2, 1),
+    ("hf224", True, "canonical", 480, 270, 1, 5, 8, 1),
+    ("hf22n", False, "canonical", 200, 150, 0, 2, 3, 1),       # mode A through the wavefront passes
+    ("hf22n", False, "canonical", 200, 150, 1, 1, 1, 0),       # a single segment
+    ("hf22n", False, "canonical", 64, 48, 1, 0, 1, 0),         # depth 0: nothing is traced
+]
+
+
+@pytest.mark.parametrize("name,sah,camera,w,h,mode,depth,spp,flags", WF_CASES)
+def test_wavefront_engine_bit_exact(clpt, oracle, renderer, scene_cache, name, sah, camera, w, h, mode, depth, spp,
+                                    flags):
+    """The wavefront engine (ray queues in HBM, persistent trace kernel with lane
+    refill) produces the same bits as the oracle -- and therefore as the megakernel."""
+    scene, _ = scene_cache(name, sah=sah)
+    cam = _cam(clpt, camera, h)
+    L = clpt.lib()
+    try:
+        L.CLSetEngine(2)
+        img, prim, t, uv = _render_gpu(renderer, scene, cam, w, h, mode=mode, depth=depth, spp=spp, seed=5,
+                                       flags=flags | clpt.FLAG_COUNTERS)
+        assert L.CLLastEngine() == 2 and L.CLLastLaunchCount() >= 3
+        got_counters = renderer.counters()
+        L.CLSetEngine(1)
+        mega = _render_gpu(renderer, scene, cam, w, h, mode=mode, depth=depth, spp=spp, seed=5, flags=flags)[0]
+        assert L.CLLastEngine() == 1
+    finally:
+        L.CLSetEngine(0)
+    ref = oracle.render(scene, cam, w, h, mode=mode, depth=depth, spp=spp, seed=5, flags=flags)
+    assert np.array_equal(prim, ref["prim"])
+    _assert_bit_equal(t, ref["t"], "t")
+    _assert_bit_equal(uv, ref["uv"], "uv")
+    _assert_bit_equal(img, ref["rgba"], "rgba")
+    _assert_bit_equal(img, mega, "wavefront vs megakernel")
+    assert got_counters == ref["counters"]
+
+
+def test_wavefront_chunking_and_sharding(clpt, oracle, renderer, scene_cache, monkeypatch):
+    """A workspace smaller than the frame (several chunks) and row-tile sharding."""
+    scene, _ = scene_cache("hf22n")
+    w, h = 200, 150
+    cam = _cam(clpt, "canonical", h)
+    full = oracle.render(scene, cam, w, h, mode=1, depth=3, spp=4, seed=9, flags=clpt.FLAG_JITTER)["rgba"]
+    L = clpt.lib()
+    monkeypatch.setenv("CLPT_WF_MAX_PATHS", str(w * 4 * 7))  # 7 rows per chunk
+    try:
+        L.CLSetEngine(2)
+        img = _render_gpu(renderer, scene, cam, w, h, aov=False, mode=1, depth=3, spp=4, seed=9,
+                          flags=clpt.FLAG_JITTER)[0]
+        _assert_bit_equal(img, full, "chunked")
+        assert L.CLLastLaunchCount() > 20
+        for rank in range(3):
+            renderer.create_image(w, h)
+            L.CLSetTileShard(rank, 3, 8)
+            renderer.execute()
+            rows = np.array([y for y in range(h) if (y // 8) % 3 == rank], dtype=int)
+            _assert_bit_equal(renderer.read_image()[rows], full[rows], f"rank {rank}")
+    finally:
+        L.CLSetTileShard(0, 1, 8)
+        L.CLSetEngine(0)
+
+
 @pytest.mark.parametrize("depth_tree", [8, 20, 24])
 def test_other_tree_depths(clpt, oracle, renderer, depth_tree):
     """The traversal is tree-agnostic: shallow and deep trees of the same mesh."""
