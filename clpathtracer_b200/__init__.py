@@ -147,7 +147,9 @@ def from_list(ptr: int, dtype, cols: int | None = None) -> np.ndarray:
         out = np.zeros(0, dtype=dt)
     else:
         n = L.list_size(ptr)
-        out = np.frombuffer(C.string_at(ptr, n), dtype=dt).copy() if n else np.zeros(0, dtype=dt)
+        out = np.empty(n // dt.itemsize, dtype=dt)
+        if n:
+            C.memmove(out.ctypes.data, ptr, n)  # (string_at cannot take sizes past 2 GiB)
     return out.reshape(-1, cols) if cols else out
 
 

@@ -29,8 +29,16 @@ CORNELL_CAMERA = dict(near=0.1, far=1.0, fov=np.pi / 3, position=(0.031, 0.047, 
 def _six_decimals(a: np.ndarray) -> np.ndarray:
     """float64 -> '%.6f' text -> float32, exactly what an OBJ round trip does."""
     flat = np.asarray(a, dtype=np.float64).reshape(-1)
-    txt = np.char.mod("%.6f", flat)
-    return txt.astype(np.float64).astype(np.float32).reshape(np.shape(a))
+    # Fast path: rint(x * 1e6) / 1e6 is the same double the text round trip gives
+    # unless x * 1e6 sits within rounding error of a .5 tie; those few values (and
+    # anything large) take the literal text path.
+    scaled = flat * 1e6
+    out = np.rint(scaled) / 1e6
+    frac = scaled - np.floor(scaled)
+    slow = (np.abs(frac - 0.5) < 1e-4) | (np.abs(flat) > 1e6) | ~np.isfinite(flat)
+    if slow.any():
+        out[slow] = np.char.mod("%.6f", flat[slow]).astype(np.float64)
+    return out.astype(np.float32).reshape(np.shape(a))
 
 
 def heightfield(n: int, with_normals: bool = False, seed: int = 0):

@@ -309,6 +309,30 @@ def test_owned_meshes_and_object_slot(clpt, oracle, renderer, scene_cache):
     assert L.CLLastLaunchCount() == 1 and L.CLLastKernelMs() > 0
 
 
+def test_scene_reupload(clpt, oracle, renderer):
+    """The animated path: CLSetMeshes again with moved geometry (exact-size
+    re-creation of every device buffer, src/CLState.c:92-102) between frames."""
+    from clpathtracer_b200 import scenes
+
+    tv, tc, _ = scenes.heightfield(30, False)
+    cam = _cam(clpt, "canonical", 120)
+    renderer.create_image(160, 120, aov=True)
+    renderer.set_params(mode=1, depth=2)
+    renderer.set_camera_matrix(cam)
+    prev = None
+    for k, builder in enumerate([clpt.build_kd, clpt.build_kd_sah, clpt.build_kd_sah]):
+        verts = tv.copy()
+        verts[:, 1] += np.float32(0.05 * k)  # the whole mesh moves up
+        scene = builder(verts, tc, None)
+        renderer.set_meshes(scene)
+        renderer.execute()
+        img = renderer.read_image()
+        ref = oracle.render(scene, cam, 160, 120, mode=1, depth=2)
+        _assert_bit_equal(img, ref["rgba"], f"frame {k}")
+        assert prev is None or not np.array_equal(prev, img)
+        prev = img
+
+
 def test_zero_matrix_and_far_camera(clpt, renderer, scene_cache):
     """Frame 0 of the reference runs with an unset matrix; a camera that misses the
     scene is all white (src/kernel.cl:421)."""
