@@ -20,6 +20,9 @@
 //             [2] = v2 - v0
 //   corners int4[3*n_prims], norms float4[]: as uploaded, only read when
 //             shading a hit with vertex normals (once per ray)
+//   lut     int[gx*gy*gz]       start-node table: a uniform grid over the root box
+//             (<= ~2M cells); entry = the deepest node that every point of the
+//             cell reaches by the root descent, so a descent may start there
 #pragma once
 
 #include <cuda_runtime.h>
@@ -43,6 +46,11 @@ struct ClptScene {
     int n_materials;
     int n_nodes, n_leaves, n_refs, n_prims, n_norms;
     float root_min[3], root_max[3];
+    // Start-node table: a uniform grid over the root box; cell -> the deepest node
+    // the whole (slightly enlarged) cell descends to.  Skips the top of the tree.
+    const int *lut;
+    int lut_dim[3];
+    float lut_scale[3]; // cells per unit length
 };
 
 struct ClptFrame {

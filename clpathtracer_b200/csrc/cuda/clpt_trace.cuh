@@ -9,6 +9,9 @@
 
 #include "clpt_device.cuh"
 
+#ifndef CLPT_START_LUT
+#define CLPT_START_LUT 1
+#endif
 #ifndef CLPT_MIN_BLOCKS
 #define CLPT_MIN_BLOCKS 8 // resident 256-thread blocks per SM the register allocation aims for (measured: 3 -> 2029, 4 -> 2488, 6 -> 2921, 8 -> 3054 Mrays/s)
 #endif
@@ -81,6 +84,23 @@ __device__ __forceinline__ bool root_clip(const ClptScene &S, V3 o, V3 inv, floa
     if (tzmin > tmin) tmin = tzmin;
     if (tzmax < tmax) tmax = tzmax;
     return tmax > 0.0f;
+}
+
+// Node to start the first descent of a ray from: the start-node table entry of
+// the grid cell holding p1 (clpt_device.cuh).  Equivalent to starting at the root.
+__device__ __forceinline__ int start_node(const ClptScene &S, V3 p1) {
+#if CLPT_START_LUT
+    // float -> int conversion saturates and maps NaN to 0, like "always left"
+    int cx = __float2int_rd(fmul(fsub(p1.x, S.root_min[0]), S.lut_scale[0]));
+    int cy = __float2int_rd(fmul(fsub(p1.y, S.root_min[1]), S.lut_scale[1]));
+    int cz = __float2int_rd(fmul(fsub(p1.z, S.root_min[2]), S.lut_scale[2]));
+    cx = min(max(cx, 0), S.lut_dim[0] - 1);
+    cy = min(max(cy, 0), S.lut_dim[1] - 1);
+    cz = min(max(cz, 0), S.lut_dim[2] - 1);
+    return __ldg(S.lut + ((size_t)cz * S.lut_dim[1] + cy) * S.lut_dim[0] + cx);
+#else
+    return 0;
+#endif
 }
 
 // Descend from node word n to the leaf containing p1, kernel.cl:325-330
@@ -174,7 +194,9 @@ __device__ __forceinline__ Hit closest_hit(const ClptScene &S, V3 o, V3 d, int m
     int visits = 0;
     float min_hit = 0.0f;
     const uint2 *__restrict__ nodes = S.nodes;
-    uint2 n = __ldg(nodes);
+    // the instrumented twin walks from the root so that its counters are the
+    // reference algorithm's visit counts (the roofline's algorithmic work)
+    uint2 n = __ldg(nodes + (COUNT ? 0 : start_node(S, p1)));
     for (;;) {
         n = descend<COUNT>(nodes, n, p1, cn);
         if (COUNT) cn.leaves++;

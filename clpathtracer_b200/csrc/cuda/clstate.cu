@@ -110,6 +110,7 @@ struct {
     DevBuf<uint2> nodes;
     DevBuf<float4> leaves, tri, norms;
     DevBuf<int4> corners;
+    DevBuf<int> lut;
     DevBuf<unsigned char> objects;
     int objcount = 0;
     DevBuf<ClptMaterial> materials;
@@ -171,6 +172,7 @@ void rebuild_scene_struct() {
     S.leaves = St.leaves.ptr;
     S.tri = St.tri.ptr;
     S.corners = St.corners.ptr;
+    S.lut = St.lut.ptr;
     S.norms = St.norms.ptr;
     S.tri_material = St.tri_material.ptr;
     S.materials = St.materials.ptr;
@@ -194,6 +196,7 @@ void upload_scene(const kdnode *nodes, size_t node_bytes, const int *tri_indices
     St.leaves.upload(reinterpret_cast<const float4 *>(packed.leaves.data()), packed.leaves.size(), St.stream);
     St.tri.upload(reinterpret_cast<const float4 *>(packed.tri.data()), packed.tri.size(), St.stream);
     St.corners.upload(reinterpret_cast<const int4 *>(tris), tri_bytes / sizeof(cl_int3), St.stream);
+    St.lut.upload(packed.lut.data(), packed.lut.size(), St.stream);
     if (n_norms) {
         St.norms.upload(reinterpret_cast<const float4 *>(norms), n_norms, St.stream);
     } else {
@@ -209,6 +212,8 @@ void upload_scene(const kdnode *nodes, size_t node_bytes, const int *tri_indices
     for (int a = 0; a < 3; a++) {
         S.root_min[a] = packed.root_min[a];
         S.root_max[a] = packed.root_max[a];
+        S.lut_dim[a] = packed.lut_dim[a];
+        S.lut_scale[a] = packed.lut_scale[a];
     }
     rebuild_scene_struct();
     St.have_scene = true;
@@ -288,7 +293,7 @@ void clpt_state_launch_frame(int width, int height) {
         F.counters = St.counters.ptr;
     }
 
-    // Engine.  Measured on the bench workload (profiles/r01_wavefront_experiment.json)
+    // Engine.  Measured on the bench workload (profiles/r01_experiments.json)
     // the megakernel with its sample-lane mapping is faster (57.7 ms against 91.3 ms
     // for the best wavefront setting), so "automatic" means megakernel; the wavefront
     // engine stays selectable and is held to the same bit-exact parity tests.
@@ -393,6 +398,7 @@ void CLTerminate(void) {
     St.tri.release();
     St.norms.release();
     St.corners.release();
+    St.lut.release();
     St.objects.release();
     St.materials.release();
     St.tri_material.release();

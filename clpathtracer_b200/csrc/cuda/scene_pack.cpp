@@ -8,6 +8,7 @@
 // triangles in the same order as the reference kernel walking the input.
 #include "scene_pack.h"
 
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 
@@ -169,6 +170,70 @@ bool clpt_pack_scene(const kdnode *nodes, size_t n_nodes, const int *tri_indices
     for (int a = 0; a < 3; a++) {
         out.root_min[a] = nodes[0].min.s[a];
         out.root_max[a] = nodes[0].max.s[a];
+    }
+    // ---- start-node table ----
+    // For a point p the kernel's descent takes child[1] iff p[axis] > plane.  Every
+    // point of a cell [lo, hi] takes the same branch at a split when hi <= plane
+    // (all left) or lo > plane (all right); the walk below follows those forced
+    // branches from the root and stops at the first split the cell straddles.  The
+    // cell is enlarged by a margin that covers the fp32 rounding of the cell index
+    // computed on the device, so starting a descent at the table entry reaches
+    // exactly the leaf a descent from the root would.
+    {
+        double ext[3], vol = 1.0;
+        for (int a = 0; a < 3; a++) {
+            ext[a] = (double)out.root_max[a] - (double)out.root_min[a];
+            if (!(ext[a] > 0)) ext[a] = 0;
+            vol *= ext[a] > 0 ? ext[a] : 1.0;
+        }
+        const double target_cells = n_nodes < 64 ? 1.0 : (n_nodes < 100000 ? 32768.0 : 2097152.0);
+        const double cell = std::cbrt(vol / target_cells);
+        size_t total = 1;
+        for (int a = 0; a < 3; a++) {
+            int d = ext[a] > 0 && cell > 0 ? (int)std::ceil(ext[a] / cell) : 1;
+            d = d < 1 ? 1 : (d > 1024 ? 1024 : d);
+            out.lut_dim[a] = d;
+            out.lut_scale[a] = ext[a] > 0 ? (float)(d / ext[a]) : 0.0f;
+            total *= (size_t)d;
+        }
+        out.lut.assign(total, 0);
+        const int gx = out.lut_dim[0], gy = out.lut_dim[1], gz = out.lut_dim[2];
+#pragma omp parallel for schedule(static) collapse(2)
+        for (int cz = 0; cz < gz; cz++) {
+            for (int cy = 0; cy < gy; cy++) {
+                for (int cx = 0; cx < gx; cx++) {
+                    const int c[3] = { cx, cy, cz };
+                    double lo[3], hi[3];
+                    for (int a = 0; a < 3; a++) {
+                        const double sc = out.lut_scale[a];
+                        const double margin = 1e-5 * (1.0 + ext[a] + std::fabs((double)out.root_min[a]));
+                        if (sc > 0) {
+                            lo[a] = (double)out.root_min[a] + c[a] / sc - margin;
+                            hi[a] = (double)out.root_min[a] + (c[a] + 1) / sc + margin;
+                        } else {
+                            lo[a] = -1e300;
+                            hi[a] = 1e300;
+                        }
+                        // the first and last cells also receive everything beyond the box
+                        if (c[a] == 0) lo[a] = -1e300;
+                        if (c[a] == out.lut_dim[a] - 1) hi[a] = 1e300;
+                    }
+                    int o = 0;
+                    while (nodes[o].type == KD_SPLIT) {
+                        const int ax = nodes[o].split.axis;
+                        const double plane = nodes[o].split.value;
+                        if (hi[ax] <= plane) {
+                            o = nodes[o].split.children[0];
+                        } else if (lo[ax] > plane) {
+                            o = nodes[o].split.children[1];
+                        } else {
+                            break;
+                        }
+                    }
+                    out.lut[((size_t)cz * gy + cy) * gx + cx] = new_of[o];
+                }
+            }
+        }
     }
     out.n_nodes = n_packed;
     out.n_leaves = n_leaves;

@@ -21,6 +21,9 @@ struct ClptPackedScene {
     std::vector<ClptFloat4> tri;    // 3 per leaf triangle slot
     float root_min[3], root_max[3];
     int n_nodes = 0, n_leaves = 0, n_refs = 0, n_prims = 0;
+    std::vector<int> lut; // start-node table, lut_dim[0] fastest
+    int lut_dim[3] = { 1, 1, 1 };
+    float lut_scale[3] = { 0, 0, 0 };
 };
 
 // Returns false and fills `err` when the input is inconsistent (index out of

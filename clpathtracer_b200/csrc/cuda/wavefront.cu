@@ -144,7 +144,7 @@ wf_trace(const __grid_constant__ ClptScene S, const float4 *__restrict__ qa, con
                     if (root_clip(S, o, inv, tmin, tmax)) {
                         p1 = o;
                         if (tmin > 0.0f) p1 = vadd(p1, vscale(d, tmin));
-                        n = __ldg(nodes);
+                        n = __ldg(nodes + (COUNT ? 0 : start_node(S, p1)));
                     } else { // missed the scene box: done before it started
                         hits[slot] = make_int2(-1, 0);
                         slot = -1;
