@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -21,6 +22,13 @@
 #include "scene_pack.h"
 
 #define CU(call) handle_err((int)(call), __FILE__, __LINE__)
+
+// gl_interop.cu
+void clpt_gl_register(unsigned int texture);
+void clpt_gl_unregister(void);
+bool clpt_gl_registered(void);
+void clpt_gl_size(int *width, int *height, cudaStream_t stream);
+void clpt_gl_present(const float4 *frame, int width, int height, cudaStream_t stream);
 
 namespace {
 
@@ -75,17 +83,24 @@ void nccl_check(ncclResult_t r, const char *file, int line) {
 template <typename T>
 struct DevBuf {
     T *ptr = nullptr;
-    size_t count = 0;
+    size_t count = 0, capacity = 0;
     void release() {
         if (ptr) CU(cudaFree(ptr));
         ptr = nullptr;
-        count = 0;
+        count = capacity = 0;
     }
-    // exact-size re-creation, like resize_buffer (src/CLState.c:92-102)
+    // The reference frees and re-creates every buffer at its exact size on each
+    // upload (resize_buffer, src/CLState.c:92-102).  cudaFree/cudaMalloc cost a
+    // device synchronisation each, which dominates re-uploads of an animated scene,
+    // so the allocation is kept while it is big enough and not more than 2x too big.
     void resize(size_t n) {
-        release();
-        if (n) CU(cudaMalloc((void **)&ptr, n * sizeof(T)));
+        if (n > capacity || n * 2 < capacity) {
+            release();
+            if (n) CU(cudaMalloc((void **)&ptr, n * sizeof(T)));
+            capacity = n;
+        }
         count = n;
+        if (n == 0) release();
     }
     void upload(const T *src, size_t n, cudaStream_t s) {
         resize(n);
@@ -183,7 +198,11 @@ void rebuild_scene_struct() {
 void upload_scene(const kdnode *nodes, size_t node_bytes, const int *tri_indices, size_t tri_index_bytes,
                   const cl_int3 *tris, size_t tri_bytes, const Vector4 *verts, size_t vert_bytes,
                   const Vector4 *norms, size_t norm_bytes) {
-    ClptPackedScene packed;
+    static ClptPackedScene packed; // keeps its vectors' capacity between uploads
+    const char *verbose = getenv("CLPT_VERBOSE");
+    const bool timing = verbose && atoi(verbose) >= 2;
+    const auto t0 = std::chrono::steady_clock::now();
+
     std::string err;
     const size_t n_norms = norms ? norm_bytes / sizeof(Vector4) : 0;
     if (!clpt_pack_scene(nodes, node_bytes / sizeof(kdnode), tri_indices, tri_index_bytes / sizeof(int), tris,
@@ -192,6 +211,7 @@ void upload_scene(const kdnode *nodes, size_t node_bytes, const int *tri_indices
         fprintf(stderr, "CLSetMeshes: invalid scene: %s\n", err.c_str());
         exit(EXIT_FAILURE);
     }
+    const auto t1 = std::chrono::steady_clock::now();
     St.nodes.upload(reinterpret_cast<const uint2 *>(packed.nodes.data()), packed.nodes.size(), St.stream);
     St.leaves.upload(reinterpret_cast<const float4 *>(packed.leaves.data()), packed.leaves.size(), St.stream);
     St.tri.upload(reinterpret_cast<const float4 *>(packed.tri.data()), packed.tri.size(), St.stream);
@@ -217,6 +237,13 @@ void upload_scene(const kdnode *nodes, size_t node_bytes, const int *tri_indices
     }
     rebuild_scene_struct();
     St.have_scene = true;
+    if (timing) {
+        const auto t2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "CLSetMeshes: pack %.3f ms, upload %.3f ms (%d nodes, %d leaves, %d triangle slots, %zu table cells)\n",
+                std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                std::chrono::duration<double, std::milli>(t2 - t1).count(), packed.n_nodes, packed.n_leaves,
+                packed.n_refs, packed.lut.size());
+    }
 }
 
 void release_host_kd() {
@@ -347,6 +374,10 @@ void clpt_state_launch_frame(int width, int height) {
         CU(cudaGetLastError());
         St.last_launches++;
     }
+    if (!St.headless && clpt_gl_registered()) {
+        clpt_gl_present(St.image.ptr, width, height, St.stream); // acquire/write/release, :207-218
+        St.last_launches++;
+    }
     CU(cudaStreamSynchronize(St.stream)); // clFinish, src/CLState.c:212
     CU(cudaEventElapsedTime(&St.last_kernel_ms, St.ev_start, St.ev_stop));
     if (St.flags & CLPT_FLAG_COUNTERS) {
@@ -393,6 +424,7 @@ void CLTerminate(void) {
         NC(g_nccl.CommDestroy(St.comm));
         St.comm = nullptr;
     }
+    if (clpt_gl_registered()) clpt_gl_unregister();
     St.nodes.release();
     St.leaves.release();
     St.tri.release();
@@ -513,6 +545,7 @@ void CLSetMaxLeafVisits(int cap) {
 void CLDeleteImage(void) {
     require_init("CLDeleteImage");
     if (!St.have_image) FATAL("CLDeleteImage: no render target"); // clReleaseMemObject(0) errors too
+    if (clpt_gl_registered()) clpt_gl_unregister();
     St.image.release();
     St.slab.release();
     St.gathered.release();
@@ -536,13 +569,12 @@ void CLCreateImageHeadless(int width, int height) {
 
 void CLCreateImage(unsigned int texture) {
     require_init("CLCreateImage");
-#ifdef CLPT_WITH_GL
-    clpt_gl_register(texture); // csrc/cuda/gl_interop.cu
-#else
-    (void)texture;
-    FATAL("CLCreateImage(GLuint): this build has no OpenGL interop (rebuild with -DCLPT_WITH_GL); "
-          "use CLCreateImageHeadless");
-#endif
+    // needs a GL context current on this thread; fails loudly otherwise (gl_interop.cu)
+    clpt_gl_register(texture);
+    clpt_gl_size(&St.width, &St.height, St.stream);
+    St.headless = false;
+    St.have_image = true;
+    alloc_targets(); // the float4 frame the kernels render into; presented to the texture per frame
 }
 
 void CLResetAccumulation(void) {

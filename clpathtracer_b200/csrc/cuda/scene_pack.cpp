@@ -186,7 +186,9 @@ bool clpt_pack_scene(const kdnode *nodes, size_t n_nodes, const int *tri_indices
             if (!(ext[a] > 0)) ext[a] = 0;
             vol *= ext[a] > 0 ? ext[a] : 1.0;
         }
-        const double target_cells = n_nodes < 64 ? 1.0 : (n_nodes < 100000 ? 32768.0 : 2097152.0);
+        // about one cell per two nodes, between 4K and 2M cells
+        double target_cells = (double)n_nodes / 2;
+        target_cells = n_nodes < 64 ? 1.0 : (target_cells < 4096.0 ? 4096.0 : (target_cells > 2097152.0 ? 2097152.0 : target_cells));
         const double cell = std::cbrt(vol / target_cells);
         size_t total = 1;
         for (int a = 0; a < 3; a++) {

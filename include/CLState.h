@@ -67,9 +67,11 @@ void CLSetMeshes(kd *models);
 void CLDeleteImage(void);
 
 /* Bind a GL_TEXTURE_2D (RGBA8) as the render target through
- * cudaGraphicsGLRegisterImage.  Only available when the library is built with
- * -DCLPT_WITH_GL (needs GL headers and a display; neither exists on the
- * build/bench machines); otherwise it fails loudly.  Replaces src/CLState.c:47-58. */
+ * cudaGraphicsGLRegisterImage; each CLExecute then maps it, writes the frame as
+ * UNORM8 texels through a surface and unmaps it (the acquire/release of
+ * src/CLState.c:207-218).  Needs an OpenGL context current on the calling
+ * thread; without one the registration fails and the call aborts with the CUDA
+ * error.  Replaces src/CLState.c:47-58. */
 void CLCreateImage(unsigned int texture);
 
 /* Render one frame of width x height pixels with the current camera, scene
