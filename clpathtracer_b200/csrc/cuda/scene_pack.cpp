@@ -83,49 +83,64 @@ bool clpt_pack_scene(const kdnode *nodes, size_t n_nodes, const int *tri_indices
     }
     const int n_packed = next;
 
-    out.nodes.assign((size_t)n_packed, ClptNode8{ 0, 0 });
-    out.leaves.assign((size_t)n_leaves * 4, ClptFloat4{ 0, 0, 0, 0 });
-    for (size_t i = 0; i < n_nodes; i++) {
+    out.nodes.resize((size_t)n_packed);
+    out.leaves.resize((size_t)n_leaves * 4);
+    long long bad_node = -1;
+    int bad_kind = 0;
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)n_nodes; i++) {
         const int ni = new_of[i];
         if (ni < 0) continue; // unreachable from the root
         const kdnode &k = nodes[i];
         if (k.type == KD_SPLIT) {
             out.nodes[ni].x = float_bits(k.split.value);
             out.nodes[ni].y = ((uint32_t)new_of[k.split.children[0]] << 2) | (uint32_t)k.split.axis;
-        } else {
-            const int li = leaf_of[i];
-            out.nodes[ni].x = (uint32_t)li;
-            out.nodes[ni].y = 3u;
-            const int first = k.leaf.tris, count = k.leaf.tri_count;
-            if (count < 0 || (count > 0 && (first < 0 || (size_t)first + (size_t)count > n_refs))) {
-                snprintf(msg, sizeof msg, "leaf node %zu references triangles [%d,+%d) of %zu", i, first,
-                         count, n_refs);
-                err = msg;
-                return false;
-            }
-            ClptFloat4 *L = &out.leaves[(size_t)li * 4];
-            L[0] = ClptFloat4{ k.min.s[0], k.min.s[1], k.min.s[2], as_float(count > 0 ? first : 0) };
-            L[1] = ClptFloat4{ k.max.s[0], k.max.s[1], k.max.s[2], as_float(count) };
-            int ropes[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-            for (int f = 0; f < 6; f++) {
-                const int r = k.leaf.ropes[f];
-                if (r == -1) {
-                    ropes[f] = -1;
-                } else if (r < 0 || (size_t)r >= n_nodes || new_of[r] < 0) {
-                    snprintf(msg, sizeof msg, "leaf node %zu rope %d -> %d is out of range", i, f, r);
-                    err = msg;
-                    return false;
-                } else {
-                    ropes[f] = new_of[r];
-                }
-            }
-            L[2] = ClptFloat4{ as_float(ropes[0]), as_float(ropes[1]), as_float(ropes[2]), as_float(ropes[3]) };
-            L[3] = ClptFloat4{ as_float(ropes[4]), as_float(ropes[5]), 0, 0 };
+            continue;
         }
+        const int li = leaf_of[i];
+        out.nodes[ni].x = (uint32_t)li;
+        out.nodes[ni].y = 3u;
+        const int first = k.leaf.tris, count = k.leaf.tri_count;
+        bool bad = count < 0 || (count > 0 && (first < 0 || (size_t)first + (size_t)count > n_refs));
+        ClptFloat4 *L = &out.leaves[(size_t)li * 4];
+        L[0] = ClptFloat4{ k.min.s[0], k.min.s[1], k.min.s[2], as_float(count > 0 ? first : 0) };
+        L[1] = ClptFloat4{ k.max.s[0], k.max.s[1], k.max.s[2], as_float(count) };
+        int ropes[6];
+        int kind = bad ? 1 : 0;
+        for (int f = 0; f < 6; f++) {
+            const int r = k.leaf.ropes[f];
+            if (r == -1) {
+                ropes[f] = -1;
+            } else if (r < 0 || (size_t)r >= n_nodes || new_of[r] < 0) {
+                ropes[f] = -1;
+                kind = 2;
+            } else {
+                ropes[f] = new_of[r];
+            }
+        }
+        L[2] = ClptFloat4{ as_float(ropes[0]), as_float(ropes[1]), as_float(ropes[2]), as_float(ropes[3]) };
+        L[3] = ClptFloat4{ as_float(ropes[4]), as_float(ropes[5]), 0, 0 };
+        if (kind) {
+#pragma omp critical(clpt_pack_err)
+            if (bad_node < 0 || i < bad_node) {
+                bad_node = i;
+                bad_kind = kind;
+            }
+        }
+    }
+    if (bad_node >= 0) {
+        const kdnode &k = nodes[bad_node];
+        if (bad_kind == 1)
+            snprintf(msg, sizeof msg, "leaf node %lld references triangles [%d,+%d) of %zu", bad_node, k.leaf.tris,
+                     k.leaf.tri_count, n_refs);
+        else
+            snprintf(msg, sizeof msg, "leaf node %lld has a rope that is out of range", bad_node);
+        err = msg;
+        return false;
     }
 
     // ---- pre-gather triangles in leaf order, edges precomputed ----
-    out.tri.assign(n_refs * 3, ClptFloat4{ 0, 0, 0, 0 });
+    out.tri.resize(n_refs * 3);
     int bad = 0;
 #pragma omp parallel for schedule(static) reduction(| : bad)
     for (long long s = 0; s < (long long)n_refs; s++) {

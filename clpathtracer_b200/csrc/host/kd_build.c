@@ -67,6 +67,60 @@ xmalloc(size_t n) {
     return p;
 }
 
+/* Build-time nodes and leaf id lists come from per-thread bump chunks that are
+ * released together when the build ends: one malloc per 256 KiB instead of two
+ * or three per node. */
+#define ARENA_CHUNK (256u << 10)
+#define ARENA_THREADS 256
+typedef struct arena_chunk {
+    struct arena_chunk *next;
+} arena_chunk;
+static arena_chunk *g_arena_chunks = NULL;
+static struct {
+    char *cur, *end;
+    char pad[48]; /* one cache line per thread */
+} g_arena[ARENA_THREADS];
+
+static int
+arena_thread(void) {
+#ifdef _OPENMP
+    extern int omp_get_thread_num(void);
+    return omp_get_thread_num() % ARENA_THREADS;
+#else
+    return 0;
+#endif
+}
+
+static void *
+arena_alloc(size_t bytes) {
+    bytes = (bytes + 15u) & ~(size_t)15u;
+    int t = arena_thread();
+    if ((size_t)(g_arena[t].end - g_arena[t].cur) < bytes) {
+        size_t payload = bytes > ARENA_CHUNK ? bytes : ARENA_CHUNK;
+        arena_chunk *c = xmalloc(sizeof(arena_chunk) + 16 + payload);
+#pragma omp critical(kd_arena)
+        {
+            c->next = g_arena_chunks;
+            g_arena_chunks = c;
+        }
+        g_arena[t].cur = (char *)c + 16 + sizeof(arena_chunk) - (sizeof(arena_chunk) % 16);
+        g_arena[t].end = (char *)c + sizeof(arena_chunk) + 16 + payload;
+    }
+    void *p = g_arena[t].cur;
+    g_arena[t].cur += bytes;
+    return p;
+}
+
+static void
+arena_release(void) {
+    while (g_arena_chunks) {
+        arena_chunk *c = g_arena_chunks;
+        g_arena_chunks = c->next;
+        free(c);
+    }
+    memset(g_arena, 0, sizeof(g_arena));
+}
+
 static tri_set
 tri_set_alloc(int n) {
     tri_set s;
@@ -102,13 +156,13 @@ tri_set_push(tri_set *dst, const tri_set *src, int t) {
 
 static bnode *
 make_leaf(const float *bmin, const float *bmax, const tri_set *s) {
-    bnode *b = xmalloc(sizeof(*b));
+    bnode *b = arena_alloc(sizeof(*b));
     memcpy(b->bmin, bmin, sizeof(b->bmin));
     memcpy(b->bmax, bmax, sizeof(b->bmax));
     b->leaf = 1;
     b->kid[0] = b->kid[1] = NULL;
     b->nids = s->n;
-    b->ids = xmalloc(sizeof(int) * (size_t)s->n);
+    b->ids = arena_alloc(sizeof(int) * (size_t)s->n);
     memcpy(b->ids, s->id, sizeof(int) * (size_t)s->n);
     return b;
 }
@@ -245,7 +299,7 @@ build_cell(tri_set s, const float *bmin, const float *bmax, int depth,
     memcpy(rmin, bmin, sizeof(rmin));
     lmax[best_axis] = rmin[best_axis] = best_v;
 
-    out = xmalloc(sizeof(*out));
+    out = arena_alloc(sizeof(*out));
     memcpy(out->bmin, bmin, sizeof(out->bmin));
     memcpy(out->bmax, bmax, sizeof(out->bmax));
     out->leaf = 0;
@@ -279,7 +333,9 @@ build_cell(tri_set s, const float *bmin, const float *bmax, int depth,
  * preorder wire format and the ropes are the same as above, so the output is
  * consumed by the same traversal.
  */
+#ifndef SAH_EXACT_BELOW
 #define SAH_EXACT_BELOW 48
+#endif
 
 typedef struct sah_params {
     int max_depth, nbins;
@@ -376,17 +432,45 @@ build_cell_sah(tri_set s, const float *bmin, const float *bmax, int depth, const
             free(hl);
             free(hr);
         } else {
-            /* every triangle bound strictly inside the cell is a candidate */
-            for (int k = 0; k < 2 * n; k++) {
-                float v = k < n ? lo[k] : hi[k - n];
+            /* Every triangle bound strictly inside the cell is a candidate.  The
+             * bounds are sorted once and the counts follow by a sweep:
+             *   NL(v) = #{lo < v} + #{flat triangles lying in the plane}
+             *   NR(v) = #{hi > v} */
+            float L[SAH_EXACT_BELOW > 0 ? SAH_EXACT_BELOW : 1], H[SAH_EXACT_BELOW > 0 ? SAH_EXACT_BELOW : 1];
+            float F[SAH_EXACT_BELOW > 0 ? SAH_EXACT_BELOW : 1];
+            int nf = 0;
+            for (int t = 0; t < n; t++) { /* insertion sorts: n <= SAH_EXACT_BELOW */
+                float x = lo[t];
+                int k = t;
+                while (k > 0 && L[k - 1] > x) { L[k] = L[k - 1]; k--; }
+                L[k] = x;
+                x = hi[t];
+                k = t;
+                while (k > 0 && H[k - 1] > x) { H[k] = H[k - 1]; k--; }
+                H[k] = x;
+                if (lo[t] == hi[t]) {
+                    x = lo[t];
+                    k = nf++;
+                    while (k > 0 && F[k - 1] > x) { F[k] = F[k - 1]; k--; }
+                    F[k] = x;
+                }
+            }
+            int il = 0, ih = 0;      /* read positions of the merged candidate stream */
+            int lo_less = 0, hi_le = 0, f0 = 0;
+            while (il < n || ih < n) {
+                float v;
+                if (ih >= n || (il < n && L[il] <= H[ih])) v = L[il++]; else v = H[ih++];
+                while (il < n && L[il] == v) il++; /* skip duplicates of this value */
+                while (ih < n && H[ih] == v) ih++;
                 if (!(v > bmin[axis] && v < bmax[axis])) {
                     continue;
                 }
-                int NL = 0, NR = 0;
-                for (int t = 0; t < n; t++) {
-                    NL += lo[t] < v || (lo[t] == hi[t] && lo[t] == v);
-                    NR += hi[t] > v;
-                }
+                while (lo_less < n && L[lo_less] < v) lo_less++;
+                while (hi_le < n && H[hi_le] <= v) hi_le++;
+                while (f0 < nf && F[f0] < v) f0++;
+                int flat_here = 0;
+                while (f0 + flat_here < nf && F[f0 + flat_here] == v) flat_here++;
+                const int NL = lo_less + flat_here, NR = n - hi_le;
                 float c = sah_cost(P, ext, axis, bmin[axis], v, NL, NR, inv_area);
                 if (c < best_cost) {
                     best_cost = c;
@@ -432,7 +516,7 @@ build_cell_sah(tri_set s, const float *bmin, const float *bmax, int depth, const
     memcpy(lmax, bmax, sizeof(lmax));
     memcpy(rmin, bmin, sizeof(rmin));
     lmax[best_axis] = rmin[best_axis] = best_v;
-    out = xmalloc(sizeof(*out));
+    out = arena_alloc(sizeof(*out));
     memcpy(out->bmin, bmin, sizeof(out->bmin));
     memcpy(out->bmax, bmax, sizeof(out->bmax));
     out->leaf = 0;
@@ -486,7 +570,6 @@ emit_preorder(emitter *em, bnode *b) {
         }
         memcpy(em->refs + em->nrefs, b->ids, sizeof(int) * (size_t)b->nids);
         em->nrefs += b->nids;
-        free(b->ids);
     } else {
         n->type = KD_SPLIT;
         n->split.value = b->value;
@@ -497,7 +580,6 @@ emit_preorder(emitter *em, bnode *b) {
         n->split.children[0] = l;
         n->split.children[1] = r;
     }
-    free(b);
     return me;
 }
 
@@ -705,6 +787,7 @@ build_tree(cl_int3 *tris, Vector3 *verts, Vector3 *norms, const char *path,
     link_cells(em.nodes, 0, links);
     tree.node_vec = em.nodes;
     tree.tri_indices = em.refs;
+    arena_release();
 
     if (path != NULL) {
         size_t len = strlen(path) + 4;
