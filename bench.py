@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--sah-ci", type=float, default=1.0)
     ap.add_argument("--sah-bonus", type=float, default=0.9)
     ap.add_argument("--sah-bins", type=int, default=32)
+    ap.add_argument("--mode", default="mirror", choices=["mirror", "path"],
+                    help="mirror: the reference's bounce (mode B); path: diffuse BSDF extension (mode C)")
     ap.add_argument("--engine", type=int, default=int(os.environ.get("CLPT_ENGINE", "0")),
                     help="0 auto, 1 megakernel, 2 wavefront")
     ap.add_argument("--tile-rows", type=int, default=8)
@@ -85,7 +87,7 @@ def workload_config(a):
                     f"heightfield n={a.grid} ({2 * a.grid * a.grid} triangles), kd builder {a.builder}, canonical camera",
         "baseline_config": a.config, "progressive": bool(a.progressive),
         "width": a.width, "height": a.height, "spp": a.spp, "depth": a.depth, "triangles": 2 * a.grid * a.grid,
-        "kd_builder": ("reference heuristic (src/kd_tree.c:95-200) at depth %d, 25 bins" % a.tree_depth) if a.builder == "ref"
+        "render_mode": a.mode, "kd_builder": ("reference heuristic (src/kd_tree.c:95-200) at depth %d, 25 bins" % a.tree_depth) if a.builder == "ref"
                       else "build_kd_sah ci=%g bonus=%g bins=%d" % (a.sah_ci, a.sah_bonus, a.sah_bins),
         "mode": "mirror (src/kernel.cl:399-417 enabled)",
         "sharding": f"row tiles of {a.tile_rows} rows, round-robin over ranks, scene replicated, NCCL all-gather",
@@ -380,10 +382,11 @@ def main():
         torch.cuda.synchronize()
 
     # instrumented frame: counts rays / node / triangle work for this rank's rows
-    r.set_params(mode=cl.MODE_MIRROR, depth=a.depth, spp=a.spp, seed=a.seed, flags=flags | cl.FLAG_COUNTERS)
+    mode = cl.MODE_PATH if a.mode == "path" else cl.MODE_MIRROR
+    r.set_params(mode=mode, depth=a.depth, spp=a.spp, seed=a.seed, flags=flags | cl.FLAG_COUNTERS)
     r.execute()
     counters = r.counters()
-    r.set_params(mode=cl.MODE_MIRROR, depth=a.depth, spp=a.spp, seed=a.seed, flags=flags)
+    r.set_params(mode=mode, depth=a.depth, spp=a.spp, seed=a.seed, flags=flags)
     totals = torch.tensor([counters[k] for k in ("rays", "splits", "leaves", "tris", "shade_vn", "capped")],
                           dtype=torch.float64, device="cuda")
     if world > 1:

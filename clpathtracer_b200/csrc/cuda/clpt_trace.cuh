@@ -9,6 +9,9 @@
 
 #include "clpt_device.cuh"
 
+#ifndef CLPT_EXPERIMENT_FMA
+#define CLPT_EXPERIMENT_FMA 0
+#endif
 #ifndef CLPT_START_LUT
 #define CLPT_START_LUT 1
 #endif
@@ -32,6 +35,14 @@ __device__ __forceinline__ V3 mk(float x, float y, float z) { V3 r = { x, y, z }
 __device__ __forceinline__ V3 vadd(V3 a, V3 b) { return mk(fadd(a.x, b.x), fadd(a.y, b.y), fadd(a.z, b.z)); }
 __device__ __forceinline__ V3 vsub(V3 a, V3 b) { return mk(fsub(a.x, b.x), fsub(a.y, b.y), fsub(a.z, b.z)); }
 __device__ __forceinline__ V3 vscale(V3 a, float k) { return mk(fmul(a.x, k), fmul(a.y, k), fmul(a.z, k)); }
+#if CLPT_EXPERIMENT_FMA
+// EXPERIMENT ONLY (never the shipped build): contracted dot/cross, to measure what
+// bit-parity with the un-contracted oracle costs.  Parity tests fail in this build.
+__device__ __forceinline__ float vdot(V3 a, V3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+__device__ __forceinline__ V3 vcross(V3 a, V3 b) {
+    return mk(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
+}
+#else
 __device__ __forceinline__ float vdot(V3 a, V3 b) {
     return fadd(fadd(fmul(a.x, b.x), fmul(a.y, b.y)), fmul(a.z, b.z));
 }
@@ -39,6 +50,7 @@ __device__ __forceinline__ V3 vcross(V3 a, V3 b) {
     return mk(fsub(fmul(a.y, b.z), fmul(a.z, b.y)), fsub(fmul(a.z, b.x), fmul(a.x, b.z)),
               fsub(fmul(a.x, b.y), fmul(a.y, b.x)));
 }
+#endif
 __device__ __forceinline__ V3 vnormalize(V3 a) {
     float len = __fsqrt_rn(vdot(a, a));
     return mk(fdiv(a.x, len), fdiv(a.y, len), fdiv(a.z, len));
