@@ -145,7 +145,7 @@ void CLFlushL2(void);                      /* overwrite a buffer larger than L2 
  * into a compact slab; CLExecute then all-gathers the slabs with NCCL and
  * de-interleaves into every rank's target.  The id is created on rank 0 with
  * CLDistGetUniqueId and carried to the others by the caller. */
-void CLDistGetUniqueId(void *id128);       /* 128 bytes out */
+void CLDistGetUniqueId(void *id128);       /* 128 bytes out; one id per CLDistInit (NCCL ids are single-use) */
 void CLDistInit(int rank, int nranks, const void *id128, int tile_rows);
 void CLDistShutdown(void);
 /* Sharding without a communicator (each rank keeps only its own rows). */

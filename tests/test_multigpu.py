@@ -1,0 +1,79 @@
+"""N > 1 on real GPUs: two ranks (one process per GPU) render their row tiles,
+CLExecute all-gathers the slabs with NCCL and de-interleaves; every rank must end
+up with the full frame, bit-identical to the single-rank frame and the oracle.
+Skipped with fewer than two devices (the CPU/gloo twin is tests/test_multirank_cpu.py)."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+WORKER = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+import clpathtracer_b200 as cl
+from clpathtracer_b200 import scenes
+from oracle import oracle_py as op
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+L = cl.lib()
+scene = cl.build_kd_sah(*scenes.heightfield(40, False))
+w, h = 250, 131                      # neither a multiple of the tile size
+cam = cl.cam_matrix(cl.make_camera(**scenes.CANONICAL_CAMERA), h)
+r = cl.Renderer(device=local)
+r.set_meshes(scene)
+r.set_camera_matrix(cam)
+def fresh_id():
+    """An NCCL unique id is good for one communicator: rank 0 makes one per CLDistInit."""
+    idbuf = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        raw = np.zeros(128, dtype=np.uint8)
+        L.CLDistGetUniqueId(raw.ctypes.data)
+        idbuf = torch.from_numpy(raw.copy())
+    idbuf = idbuf.cuda()
+    dist.broadcast(idbuf, 0)
+    return idbuf.cpu().numpy().copy()
+
+ok = True
+for tile_rows, engine in ((8, 1), (4, 1), (8, 2)):
+    raw = fresh_id()
+    L.CLDistInit(rank, world, raw.ctypes.data, tile_rows)
+    L.CLSetEngine(engine)
+    r.set_params(mode=1, depth=4, spp=5, seed=3, flags=cl.FLAG_JITTER)
+    r.create_image(w, h)
+    r.execute()
+    img = r.read_image()
+    ref = op.render(scene, cam, w, h, mode=1, depth=4, spp=5, seed=3, flags=op.FLAG_JITTER, aov=False)["rgba"]
+    same = np.array_equal(img.view(np.uint32), ref.view(np.uint32))
+    print(f"rank {rank} tile_rows {tile_rows} engine {engine}: {'ok' if same else 'MISMATCH'}", flush=True)
+    ok = ok and same
+    L.CLDistShutdown()
+r.close()
+flag = torch.tensor([1 if ok else 0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+dist.destroy_process_group()
+sys.exit(0 if int(flag.item()) == 1 else 1)
+'''
+
+
+@pytest.mark.gpu
+def test_two_rank_nccl_gather(tmp_path):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": str(ROOT)})
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29541", str(script)]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert p.stdout.count(": ok") == 6, p.stdout
