@@ -7,7 +7,7 @@
 //   nodes   uint2[n_nodes]   8 B per node, siblings adjacent
 //             split: x = float bits of the plane, y = (first_child << 2) | axis
 //                    children are first_child (p <= plane) and first_child+1
-//             leaf : x = leaf record index,        y = 3
+//             leaf : x = leaf record index,        y = 0x80000003 (bit 31 set)
 //   leaves  float4[4*n_leaves]  64 B per leaf, 64-byte aligned
 //             [0] = min.xyz, int bits of the first triangle slot
 //             [1] = max.xyz, int bits of the triangle count
@@ -27,6 +27,8 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#define CLPT_LEAF_WORD 0x80000003u
 
 struct ClptMaterial {
     float albedo[3];

@@ -119,10 +119,9 @@ __device__ __forceinline__ int start_node(const ClptScene &S, V3 p1) {
 // (selects, no branches).  Returns the leaf's node word.
 template <bool COUNT>
 __device__ __forceinline__ uint2 descend(const uint2 *__restrict__ nodes, uint2 n, V3 p1, Counters &cn) {
-    while ((n.y & 3u) != 3u) {
-        const unsigned axis = n.y & 3u;
-        float p = axis == 1u ? p1.y : p1.x;
-        p = axis == 2u ? p1.z : p;
+    while ((int)n.y >= 0) { // bit 31 marks a leaf: one sign test
+        float p = (n.y & 1u) ? p1.y : p1.x; // bits 0-1: axis, tested bit by bit
+        p = (n.y & 2u) ? p1.z : p;
         const unsigned index = (n.y >> 2) + (p > __uint_as_float(n.x) ? 1u : 0u);
         n = __ldg(nodes + index);
         if (COUNT) cn.splits++;
@@ -130,28 +129,34 @@ __device__ __forceinline__ uint2 descend(const uint2 *__restrict__ nodes, uint2 
     return n;
 }
 
-// Leaf slab interval and exit face, kernel.cl:146-174.
-__device__ __forceinline__ void leaf_interval(float4 lmin, float4 lmax, V3 o, V3 inv, float &tmin, float &tmax,
-                                              int &far) {
+// Leaf slab interval, kernel.cl:146-174, in two halves.  The exit half (tmax and
+// the face the ray leaves by) is needed at every leaf; the entry half (tmin) only
+// feeds the early-out test, which can only fire once a hit exists, so it is
+// evaluated lazily.  Same expressions, same order, as the single function.
+__device__ __forceinline__ void leaf_exit(float4 lmin, float4 lmax, V3 o, V3 inv, float &tmax, int &far) {
     const bool sx = inv.x < 0.0f, sy = inv.y < 0.0f, sz = inv.z < 0.0f;
     far = sx ? 0 : 1;
-    const float nx = sx ? lmax.x : lmin.x, fx = sx ? lmin.x : lmax.x;
-    const float ny = sy ? lmax.y : lmin.y, fy = sy ? lmin.y : lmax.y;
-    const float nz = sz ? lmax.z : lmin.z, fz = sz ? lmin.z : lmax.z;
-    tmin = fmul(fsub(nx, o.x), inv.x);
-    tmax = fmul(fsub(fx, o.x), inv.x);
-    const float tymin = fmul(fsub(ny, o.y), inv.y), tymax = fmul(fsub(fy, o.y), inv.y);
-    if (tymin > tmin) tmin = tymin;
+    tmax = fmul(fsub(sx ? lmin.x : lmax.x, o.x), inv.x);
+    const float tymax = fmul(fsub(sy ? lmin.y : lmax.y, o.y), inv.y);
     if (tymax < tmax) {
         tmax = tymax;
         far = sy ? 2 : 3;
     }
-    const float tzmin = fmul(fsub(nz, o.z), inv.z), tzmax = fmul(fsub(fz, o.z), inv.z);
-    if (tzmin > tmin) tmin = tzmin;
+    const float tzmax = fmul(fsub(sz ? lmin.z : lmax.z, o.z), inv.z);
     if (tzmax < tmax) {
         tmax = tzmax;
         far = sz ? 4 : 5;
     }
+}
+
+__device__ __forceinline__ float leaf_entry(float4 lmin, float4 lmax, V3 o, V3 inv) {
+    const bool sx = inv.x < 0.0f, sy = inv.y < 0.0f, sz = inv.z < 0.0f;
+    float tmin = fmul(fsub(sx ? lmax.x : lmin.x, o.x), inv.x);
+    const float tymin = fmul(fsub(sy ? lmax.y : lmin.y, o.y), inv.y);
+    if (tymin > tmin) tmin = tymin;
+    const float tzmin = fmul(fsub(sz ? lmax.z : lmin.z, o.z), inv.z);
+    if (tzmin > tmin) tmin = tzmin;
+    return tmin;
 }
 
 // Triangle run of a leaf, kernel.cl:333-368 / 227-255.  Early exits are kept as
@@ -217,14 +222,14 @@ __device__ __forceinline__ Hit closest_hit(const ClptScene &S, V3 o, V3 d, int m
         // The exit depends only on the leaf box and the ray, so it is evaluated BEFORE
         // the triangle run: three values stay live across the run instead of eight.
         int far;
-        leaf_interval(lmin, lmax, o, inv, tmin, tmax, far);
+        leaf_exit(lmin, lmax, o, inv, tmax, far);
         // The neighbour across the exit face and its node word are requested now, so
         // the two dependent loads overlap the triangle run instead of following it.
         const int next = __ldg(reinterpret_cast<const int *>(L + 2) + far);
-        uint2 n_next = make_uint2(0u, 3u);
+        uint2 n_next = make_uint2(0u, CLPT_LEAF_WORD);
         if (next >= 0) n_next = __ldg(nodes + next);
         triangle_run<COUNT>(S.tri, __float_as_int(lmin.w), __float_as_int(lmax.w), o, d, h.ref, min_hit, cn);
-        if (hit_is_final(h.ref, tmin, min_hit)) break;
+        if (h.ref >= 0 && hit_is_final(h.ref, leaf_entry(__ldg(L), __ldg(L + 1), o, inv), min_hit)) break;
         p1 = vadd(o, vscale(d, tmax)); // :385
         if (next == -1) break;
         if (++visits >= max_visits) {

@@ -40,8 +40,8 @@ bool clpt_pack_scene(const kdnode *nodes, size_t n_nodes, const int *tri_indices
         err = "empty node array";
         return false;
     }
-    if (n_nodes >= (1u << 30)) {
-        err = "too many nodes for the 30-bit child field";
+    if (n_nodes >= (1u << 29)) {
+        err = "too many nodes for the 29-bit child field";
         return false;
     }
     const size_t n_prims = n_corners / 3;
@@ -99,7 +99,7 @@ bool clpt_pack_scene(const kdnode *nodes, size_t n_nodes, const int *tri_indices
         }
         const int li = leaf_of[i];
         out.nodes[ni].x = (uint32_t)li;
-        out.nodes[ni].y = 3u;
+        out.nodes[ni].y = 0x80000003u; // CLPT_LEAF_WORD
         const int first = k.leaf.tris, count = k.leaf.tri_count;
         bool bad = count < 0 || (count > 0 && (first < 0 || (size_t)first + (size_t)count > n_refs));
         ClptFloat4 *L = &out.leaves[(size_t)li * 4];

@@ -107,7 +107,7 @@ wf_trace(const __grid_constant__ ClptScene S, const float4 *__restrict__ qa, con
 
     int slot = -1;
     V3 o = mk(0, 0, 0), d = mk(0, 0, 0), inv = mk(0, 0, 0), p1 = mk(0, 0, 0);
-    uint2 n = make_uint2(0u, 3u);
+    uint2 n = make_uint2(0u, CLPT_LEAF_WORD);
     int ref = -1, visits = 0;
     float min_hit = 0.0f;
     unsigned w_next = 0, w_end = 0; // this warp's window of the queue (warp-uniform)
@@ -162,14 +162,14 @@ wf_trace(const __grid_constant__ ClptScene S, const float4 *__restrict__ qa, con
             if (COUNT) cn.leaves++;
             const float4 *L = S.leaves + 4 * (size_t)n.x;
             const float4 lmin = __ldg(L), lmax = __ldg(L + 1);
-            float tmin, tmax;
+            float tmax;
             int far;
-            leaf_interval(lmin, lmax, o, inv, tmin, tmax, far);
+            leaf_exit(lmin, lmax, o, inv, tmax, far);
             const int next = __ldg(reinterpret_cast<const int *>(L + 2) + far);
-            uint2 n_next = make_uint2(0u, 3u);
+            uint2 n_next = make_uint2(0u, CLPT_LEAF_WORD);
             if (next >= 0) n_next = __ldg(nodes + next);
             triangle_run<COUNT>(S.tri, __float_as_int(lmin.w), __float_as_int(lmax.w), o, d, ref, min_hit, cn);
-            bool done = hit_is_final(ref, tmin, min_hit);
+            bool done = ref >= 0 && hit_is_final(ref, leaf_entry(__ldg(L), __ldg(L + 1), o, inv), min_hit);
             if (!done) {
                 p1 = vadd(o, vscale(d, tmax));
                 done = next == -1;
