@@ -80,6 +80,8 @@ void nccl_check(ncclResult_t r, const char *file, int line) {
 }
 #define NC(call) nccl_check((call), __FILE__, __LINE__)
 
+ClptPackedScene g_packed; // host staging of the re-laid-out scene (page-locked once CLInit ran)
+
 template <typename T>
 struct DevBuf {
     T *ptr = nullptr;
@@ -198,7 +200,7 @@ void rebuild_scene_struct() {
 void upload_scene(const kdnode *nodes, size_t node_bytes, const int *tri_indices, size_t tri_index_bytes,
                   const cl_int3 *tris, size_t tri_bytes, const Vector4 *verts, size_t vert_bytes,
                   const Vector4 *norms, size_t norm_bytes) {
-    static ClptPackedScene packed; // keeps its vectors' capacity between uploads
+    ClptPackedScene &packed = g_packed; // keeps its staging capacity between uploads
     const char *verbose = getenv("CLPT_VERBOSE");
     const bool timing = verbose && atoi(verbose) >= 2;
     const auto t0 = std::chrono::steady_clock::now();
@@ -245,6 +247,13 @@ void upload_scene(const kdnode *nodes, size_t node_bytes, const int *tri_indices
                 packed.n_refs, packed.lut.size());
     }
 }
+
+void *pinned_alloc(size_t bytes) {
+    void *p = nullptr;
+    CU(cudaMallocHost(&p, bytes));
+    return p;
+}
+void pinned_free(void *p) { (void)cudaFreeHost(p); } // may run during process teardown: never fatal
 
 void release_host_kd() {
     if (St.owns_kd) delete_kd(St.host_kd);
@@ -413,6 +422,8 @@ void CLInit(const char *kernel_filename, const char *kernel_name) {
     CU(cudaEventCreate(&St.ev_stop));
     for (auto &e : St.ev_user) CU(cudaEventCreate(&e));
     memset(St.cam, 0, sizeof(St.cam));
+    clpt_pack_alloc = pinned_alloc; // the packed scene is staged in page-locked memory
+    clpt_pack_free = pinned_free;
     St.inited = true;
 }
 
@@ -445,6 +456,10 @@ void CLTerminate(void) {
     St.l2_flush.release();
     St.wf_workspace.release();
     St.wf_max_paths = 0;
+    g_packed.nodes.release();
+    g_packed.leaves.release();
+    g_packed.tri.release();
+    g_packed.lut.release();
     CU(cudaEventDestroy(St.ev_start));
     CU(cudaEventDestroy(St.ev_stop));
     for (auto &e : St.ev_user) CU(cudaEventDestroy(e));

@@ -10,7 +10,11 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+
+clpt_host_alloc_fn clpt_pack_alloc = malloc;
+clpt_host_free_fn clpt_pack_free = free;
 
 namespace {
 
@@ -213,7 +217,7 @@ bool clpt_pack_scene(const kdnode *nodes, size_t n_nodes, const int *tri_indices
             out.lut_scale[a] = ext[a] > 0 ? (float)(d / ext[a]) : 0.0f;
             total *= (size_t)d;
         }
-        out.lut.assign(total, 0);
+        out.lut.resize(total);
         const int gx = out.lut_dim[0], gy = out.lut_dim[1], gz = out.lut_dim[2];
 #pragma omp parallel for schedule(static) collapse(2)
         for (int cz = 0; cz < gz; cz++) {

@@ -333,6 +333,46 @@ def test_scene_reupload(clpt, oracle, renderer):
         prev = img
 
 
+def test_clhandler_layer_and_leaf_cap(clpt, oracle, renderer, scene_cache):
+    """The CLHandler.h wrappers (the reference's runtime layer, include/CLHandler.h:6-25)
+    drive the same launch as CLExecute; the rope-hop cap matches the oracle's."""
+    scene, _ = scene_cache("hf22n")
+    cam = _cam(clpt, "canonical", 96)
+    L = clpt.lib()
+    renderer.set_meshes(scene)
+    renderer.set_camera_matrix(cam)
+    renderer.set_params(mode=1, depth=2)
+    renderer.create_image(128, 96)
+    for fn, res, args in [("CLGetPlatform", C.c_void_p, []), ("CLGetDevice", C.c_void_p, [C.c_void_p]),
+                          ("CLCreateKernel", C.c_void_p, [C.c_char_p, C.c_void_p]),
+                          ("CLCreateBuffer", C.c_void_p, [C.c_void_p, C.c_size_t]),
+                          ("CLReleaseBuffer", None, [C.c_void_p]),
+                          ("CLEnqueueKernel", None, [C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                          ("err_string", C.c_char_p, [C.c_int])]:
+        getattr(L, fn).restype, getattr(L, fn).argtypes = res, args
+    plat = L.CLGetPlatform()
+    assert L.CLGetDevice(plat)
+    kern = L.CLCreateKernel(b"render", None)
+    buf = L.CLCreateBuffer(None, 4096)
+    assert buf
+    L.CLReleaseBuffer(buf)
+    size = (C.c_size_t * 2)(128, 96)
+    L.CLEnqueueKernel(2, size, None, None, kern)  # global = {w, h}, local = NULL (src/CLState.c:209-211)
+    ref = oracle.render(scene, cam, 128, 96, mode=1, depth=2)
+    _assert_bit_equal(renderer.read_image(), ref["rgba"], "CLEnqueueKernel frame")
+    assert L.err_string(2) == b"cudaErrorMemoryAllocation" and L.err_string(0) == b"cudaSuccess"
+    try:
+        L.CLSetMaxLeafVisits(2)
+        renderer.set_params(mode=1, depth=2, flags=clpt.FLAG_COUNTERS)
+        renderer.execute()
+        capped = oracle.render(scene, cam, 128, 96, mode=1, depth=2, max_leaf_visits=2)
+        _assert_bit_equal(renderer.read_image(), capped["rgba"], "capped frame")
+        assert renderer.counters() == capped["counters"] and capped["counters"]["capped"] > 0
+    finally:
+        L.CLSetMaxLeafVisits(4096)
+        renderer.set_params()
+
+
 def test_zero_matrix_and_far_camera(clpt, renderer, scene_cache):
     """Frame 0 of the reference runs with an unset matrix; a camera that misses the
     scene is all white (src/kernel.cl:421)."""
