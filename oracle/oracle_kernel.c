@@ -4,11 +4,19 @@
  * cpu_baseline / --impl reference legs may load this.  It is the checker for
  * the CUDA path, never a fallback for it.
  *
- * PARITY STATUS: "parity unpinned" for this file.  The reference's device
- * code (src/kernel.cl) cannot be compiled or run in this image (no OpenCL
- * headers, ICD or clang; gcc/g++ reject its OpenCL-C vector syntax), and the
- * reference ships no tests, golden images or fixtures.  What follows is a
- * line-by-line restatement in C of
+ * PARITY STATUS.  The reference ships no tests, golden images or fixtures, and
+ * its device code (src/kernel.cl) cannot be compiled in the build container (no
+ * OpenCL headers, ICD or clang; gcc/g++ reject its OpenCL-C vector syntax).
+ *   mode A (as shipped)  PINNED by a run of the reference's own kernel.cl on the
+ *        B200 through the driver's OpenCL ICD (oracle/cl_harness.c; frames
+ *        committed as tests/golden/ref_kernel_golden.npz and re-run live by
+ *        tests/test_reference_kernel.py): same triangle at every pixel except exact
+ *        edge-graze ties, same-triangle colours within 1 ulp (the vendor compiler
+ *        contracts FMAs, this file does not).
+ *   mode B (the code after the early return), jitter, multi-spp, mode C:
+ *        "parity unpinned" -- the reference never executes them; this file is the
+ *        definition.  Mode B's primary hits are mode A's.
+ * What follows is a line-by-line restatement in C of
  *     src/kernel.cl:79-87    new_Ray
  *     src/kernel.cl:89-94    mul (matrix * point with perspective divide)
  *     src/kernel.cl:101-144  hit_AABB
