@@ -590,12 +590,19 @@ emit_preorder(emitter *em, bnode *b) {
  * does not cut this cell's extent on that axis; then the two children link to
  * each other across the split plane. */
 static void
-push_down_link(const kdnode *nodes, const kdnode *cell, int face, int *link) {
+push_down_link(const kdnode *nodes, const kdnode *cell, int face, int *link, int full) {
     while (*link != -1 && nodes[*link].type != KD_LEAF) {
         const kdnode *nb = &nodes[*link];
         int ax = nb->split.axis;
         if (face / 2 == ax) {
-            return;
+            if (!full) {
+                return; /* the reference stops here (src/kd_tree.c:49-51) */
+            }
+            /* A split parallel to the face: only the child touching the face can
+             * be entered through it -- the low child when the neighbour lies above
+             * this cell (face on our max side), the high child otherwise. */
+            *link = nb->split.children[(face & 1) ? 0 : 1];
+            continue;
         }
         float plane = nb->split.value;
         if (plane >= cell->max.s[ax]) {
@@ -608,15 +615,24 @@ push_down_link(const kdnode *nodes, const kdnode *cell, int face, int *link) {
     }
 }
 
+/* full = 0: the reference's rope construction, byte for byte.  full = 1 (SAH
+ * builder only): links are also pushed through splits parallel to their face and
+ * once more at the leaves, so a ray that leaves a leaf lands deeper in the
+ * neighbour's subtree and re-descends less. */
 static void
-link_cells(kdnode *nodes, int index, int links[6]) {
+link_cells(kdnode *nodes, int index, int links[6], int full) {
     kdnode *cell = &nodes[index];
     if (cell->type == KD_LEAF) {
+        if (full) {
+            for (int f = 0; f < 6; f++) {
+                push_down_link(nodes, cell, f, &links[f], 1);
+            }
+        }
         memcpy(cell->leaf.ropes, links, sizeof(int) * 6);
         return;
     }
     for (int f = 0; f < 6; f++) {
-        push_down_link(nodes, cell, f, &links[f]);
+        push_down_link(nodes, cell, f, &links[f], full);
     }
     int ax = cell->split.axis;
     int lo_child = cell->split.children[0], hi_child = cell->split.children[1];
@@ -625,8 +641,8 @@ link_cells(kdnode *nodes, int index, int links[6]) {
     memcpy(hi_links, links, sizeof(hi_links));
     lo_links[2 * ax + 1] = hi_child; /* max face of the low child */
     hi_links[2 * ax] = lo_child;     /* min face of the high child */
-    link_cells(nodes, lo_child, lo_links);
-    link_cells(nodes, hi_child, hi_links);
+    link_cells(nodes, lo_child, lo_links, full);
+    link_cells(nodes, hi_child, hi_links, full);
 }
 
 int
@@ -784,7 +800,7 @@ build_tree(cl_int3 *tris, Vector3 *verts, Vector3 *norms, const char *path,
     em.nnodes = em.nrefs = 0;
     emit_preorder(&em, top);
     int links[6] = { -1, -1, -1, -1, -1, -1 };
-    link_cells(em.nodes, 0, links);
+    link_cells(em.nodes, 0, links, sah != NULL);
     tree.node_vec = em.nodes;
     tree.tri_indices = em.refs;
     arena_release();
