@@ -373,6 +373,40 @@ def test_clhandler_layer_and_leaf_cap(clpt, oracle, renderer, scene_cache):
         renderer.set_params()
 
 
+@pytest.mark.parametrize("sah", [False, True])
+def test_degenerate_rays_and_random_views(clpt, oracle, renderer, scene_cache, sah):
+    """Axis-aligned views (direction components exactly 0 -> infinite reciprocals,
+    0*inf = NaN in the slab tests), eyes sitting exactly on mesh/grid planes, eyes
+    inside the scene box, and a batch of random cameras: the NaN/inf behaviour of
+    every comparison must match the oracle's."""
+    rng = np.random.default_rng(11)
+    views = [
+        dict(position=(0.0, 1.5, 0.0), forward=(0.0, -1.0, 1e-9)),     # straight down (forward.x == 0 exactly)
+        dict(position=(0.0, 0.05, -1.0), forward=(0.0, 0.0, 1.0)),      # along +z in the x = 0 plane, on the box face
+        dict(position=(-1.0, 0.1, 0.0), forward=(1.0, 0.0, 0.0)),       # along +x from the box face
+        dict(position=(0.25, 0.0, 0.25), forward=(0.6, 0.0, 0.8)),      # horizontal, inside the box
+        dict(position=(0.0, -0.5, 0.0), forward=(0.0, 1.0, 1e-9)),      # from below: every face is a back face
+    ]
+    for _ in range(6):
+        f = rng.normal(size=3)
+        views.append(dict(position=tuple(rng.uniform(-1.5, 1.5, 3)), forward=tuple(f / np.linalg.norm(f))))
+    for name in ("hf22", "soup500"):
+        scene, _ = scene_cache(name, sah=sah)
+        renderer.set_meshes(scene)
+        renderer.set_params(mode=1, depth=4)
+        renderer.create_image(96, 64, aov=True)
+        for k, v in enumerate(views):
+            cam = clpt.cam_matrix(clpt.make_camera(near=0.1, far=1.0, fov=1.0, **v), 64)
+            renderer.set_camera_matrix(cam)
+            renderer.execute()
+            img = renderer.read_image()
+            prim, t, uv = renderer.read_aov()
+            ref = oracle.render(scene, cam, 96, 64, mode=1, depth=4)
+            assert np.array_equal(prim, ref["prim"]), (name, k)
+            _assert_bit_equal(t, ref["t"], f"{name} view {k} t")
+            _assert_bit_equal(img, ref["rgba"], f"{name} view {k} rgba")
+
+
 def test_zero_matrix_and_far_camera(clpt, renderer, scene_cache):
     """Frame 0 of the reference runs with an unset matrix; a camera that misses the
     scene is all white (src/kernel.cl:421)."""
