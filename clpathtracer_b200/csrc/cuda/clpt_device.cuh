@@ -11,7 +11,8 @@
 //   leaves  float4[4*n_leaves]  64 B per leaf, 64-byte aligned
 //             [0] = min.xyz, int bits of the first triangle slot
 //             [1] = max.xyz, int bits of the triangle count
-//             [2] = ropes 0..3 (int bits; node index in `nodes`, -1 = outside)
+//             [2] = ropes 0..3 (int bits; >= 0: node index in `nodes`; -1: outside;
+//                   <= -2: the neighbour is itself a leaf, record -2 - value)
 //             [3] = ropes 4..5, 0, 0
 //   tri     float4[3*n_refs]    48 B per leaf triangle slot, in leaf order, so a
 //                               leaf's triangles are one contiguous run

@@ -226,7 +226,7 @@ __device__ __forceinline__ Hit closest_hit(const ClptScene &S, V3 o, V3 d, int m
         // The neighbour across the exit face and its node word are requested now, so
         // the two dependent loads overlap the triangle run instead of following it.
         const int next = __ldg(reinterpret_cast<const int *>(L + 2) + far);
-        uint2 n_next = make_uint2(0u, CLPT_LEAF_WORD);
+        uint2 n_next = make_uint2((unsigned)(-2 - next), CLPT_LEAF_WORD); // neighbour is a leaf: its word is implied
         if (next >= 0) n_next = __ldg(nodes + next);
         triangle_run<COUNT>(S.tri, __float_as_int(lmin.w), __float_as_int(lmax.w), o, d, h.ref, min_hit, cn);
         if (h.ref >= 0 && hit_is_final(h.ref, leaf_entry(__ldg(L), __ldg(L + 1), o, inv), min_hit)) break;

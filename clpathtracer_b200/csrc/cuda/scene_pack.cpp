@@ -118,6 +118,8 @@ bool clpt_pack_scene(const kdnode *nodes, size_t n_nodes, const int *tri_indices
             } else if (r < 0 || (size_t)r >= n_nodes || new_of[r] < 0) {
                 ropes[f] = -1;
                 kind = 2;
+            } else if (nodes[r].type == KD_LEAF) {
+                ropes[f] = -2 - leaf_of[r]; // straight to the leaf record: no node word to fetch
             } else {
                 ropes[f] = new_of[r];
             }
