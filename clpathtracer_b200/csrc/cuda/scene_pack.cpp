@@ -8,6 +8,11 @@
 // triangles in the same order as the reference kernel walking the input.
 #include "scene_pack.h"
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -17,6 +22,17 @@ clpt_host_alloc_fn clpt_pack_alloc = malloc;
 clpt_host_free_fn clpt_pack_free = free;
 
 namespace {
+
+struct PackTimer {
+    bool on = getenv("CLPT_PACK_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char *what) {
+        if (!on) return;
+        auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "  pack %-12s %.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
 
 inline int as_int(float f) {
     int i;
@@ -40,6 +56,7 @@ bool clpt_pack_scene(const kdnode *nodes, size_t n_nodes, const int *tri_indices
                      const cl_int3 *corners, size_t n_corners, const Vector4 *verts, size_t n_verts,
                      size_t n_norms, ClptPackedScene &out, std::string &err) {
     char msg[256];
+    PackTimer timer;
     if (n_nodes == 0) {
         err = "empty node array";
         return false;
@@ -50,42 +67,98 @@ bool clpt_pack_scene(const kdnode *nodes, size_t n_nodes, const int *tri_indices
     }
     const size_t n_prims = n_corners / 3;
 
-    // ---- renumber nodes: depth-first, siblings adjacent ----
+    // ---- renumber nodes: siblings adjacent, pairs in the order of their parents ----
+    // The children of the k-th split node (in input order) become nodes 1+2k and
+    // 2+2k.  For the preorder arrays the builders emit this is the depth-first pair
+    // order (a subtree's pairs are contiguous); for any other input it is still a
+    // valid numbering.  Ranks come from parallel prefix sums over the node types.
     std::vector<int> new_of(n_nodes, -1), leaf_of(n_nodes, -1);
-    int n_leaves = 0;
-    for (size_t i = 0; i < n_nodes; i++) {
-        if (nodes[i].type == KD_LEAF) {
-            leaf_of[i] = n_leaves++; // preorder rank: neighbours in space stay neighbours in memory
-        } else if (nodes[i].type != KD_SPLIT) {
-            snprintf(msg, sizeof msg, "node %zu has type %d", i, nodes[i].type);
+    int n_leaves = 0, n_splits = 0;
+    {
+        int nthreads = 1;
+#ifdef _OPENMP
+        nthreads = omp_get_max_threads();
+#endif
+        std::vector<long long> split_base((size_t)nthreads + 1, 0), leaf_base((size_t)nthreads + 1, 0);
+        long long bad_type = -1;
+#pragma omp parallel num_threads(nthreads)
+        {
+            int t = 0, nt = 1;
+#ifdef _OPENMP
+            t = omp_get_thread_num();
+            nt = omp_get_num_threads();
+#endif
+            const size_t lo = n_nodes * (size_t)t / nt, hi = n_nodes * (size_t)(t + 1) / nt;
+            long long ns = 0, nl = 0;
+            for (size_t i = lo; i < hi; i++) {
+                if (nodes[i].type == KD_SPLIT) ns++;
+                else if (nodes[i].type == KD_LEAF) nl++;
+                else {
+#pragma omp critical(clpt_pack_err)
+                    if (bad_type < 0 || (long long)i < bad_type) bad_type = (long long)i;
+                }
+            }
+            split_base[t + 1] = ns;
+            leaf_base[t + 1] = nl;
+#pragma omp barrier
+#pragma omp single
+            for (int k = 0; k < nt; k++) {
+                split_base[k + 1] += split_base[k];
+                leaf_base[k + 1] += leaf_base[k];
+            }
+            long long ks = split_base[t], kl = leaf_base[t];
+            for (size_t i = lo; i < hi; i++) {
+                if (nodes[i].type == KD_SPLIT) {
+                    const int c0 = nodes[i].split.children[0], c1 = nodes[i].split.children[1];
+                    if (c0 > 0 && c1 > 0 && (size_t)c0 < n_nodes && (size_t)c1 < n_nodes && c0 != c1) {
+                        new_of[c0] = (int)(1 + 2 * ks); // each child has one parent: no two threads write one slot
+                        new_of[c1] = (int)(2 + 2 * ks);
+                    }
+                    ks++;
+                } else if (nodes[i].type == KD_LEAF) {
+                    leaf_of[i] = (int)kl++; // input order: neighbours in space stay neighbours in memory
+                }
+            }
+            if (t == nt - 1) {
+                n_splits = (int)split_base[nt];
+                n_leaves = (int)leaf_base[nt];
+            }
+        }
+        if (bad_type >= 0) {
+            snprintf(msg, sizeof msg, "node %lld has type %d", bad_type, nodes[bad_type].type);
             err = msg;
             return false;
         }
     }
-    std::vector<int> stack;
-    stack.reserve(128);
-    int next = 1;
     new_of[0] = 0;
-    stack.push_back(0);
-    while (!stack.empty()) {
-        const int o = stack.back();
-        stack.pop_back();
-        if (nodes[o].type != KD_SPLIT) continue;
-        const int c0 = nodes[o].split.children[0], c1 = nodes[o].split.children[1];
-        if (c0 < 0 || c1 < 0 || (size_t)c0 >= n_nodes || (size_t)c1 >= n_nodes || new_of[c0] != -1 ||
-            new_of[c1] != -1 || nodes[o].split.axis < 0 || nodes[o].split.axis > 2) {
-            snprintf(msg, sizeof msg, "split node %d is malformed (children %d,%d axis %d)", o, c0, c1,
-                     nodes[o].split.axis);
+    // every split must own exactly the pair its rank says (catches malformed or shared children)
+    {
+        long long bad_split = -1;
+        long long ks_check = 0;
+        (void)ks_check;
+#pragma omp parallel for schedule(static)
+        for (long long i = 0; i < (long long)n_nodes; i++) {
+            if (nodes[i].type != KD_SPLIT) continue;
+            const int c0 = nodes[i].split.children[0], c1 = nodes[i].split.children[1];
+            const int ax = nodes[i].split.axis;
+            bool ok = c0 > 0 && c1 > 0 && (size_t)c0 < n_nodes && (size_t)c1 < n_nodes && c0 != c1 && ax >= 0 && ax <= 2;
+            if (ok) ok = new_of[c1] == new_of[c0] + 1 && (new_of[c0] & 1) == 1;
+            if (!ok) {
+#pragma omp critical(clpt_pack_err)
+                if (bad_split < 0 || i < bad_split) bad_split = i;
+            }
+        }
+        if (bad_split >= 0) {
+            const kdnode &k = nodes[bad_split];
+            snprintf(msg, sizeof msg, "split node %lld is malformed (children %d,%d axis %d)", bad_split,
+                     k.split.children[0], k.split.children[1], k.split.axis);
             err = msg;
             return false;
         }
-        new_of[c0] = next;
-        new_of[c1] = next + 1;
-        next += 2;
-        stack.push_back(c1);
-        stack.push_back(c0);
     }
+    const int next = 1 + 2 * n_splits;
     const int n_packed = next;
+    timer.lap("renumber");
 
     out.nodes.resize((size_t)n_packed);
     out.leaves.resize((size_t)n_leaves * 4);
@@ -145,6 +218,7 @@ bool clpt_pack_scene(const kdnode *nodes, size_t n_nodes, const int *tri_indices
         return false;
     }
 
+    timer.lap("nodes+leaves");
     // ---- pre-gather triangles in leaf order, edges precomputed ----
     out.tri.resize(n_refs * 3);
     int bad = 0;
@@ -173,6 +247,7 @@ bool clpt_pack_scene(const kdnode *nodes, size_t n_nodes, const int *tri_indices
         err = (bad & 1) ? "tri_indices entry out of range" : "triangle corner references a missing vertex";
         return false;
     }
+    timer.lap("triangles");
     // vertex-normal indices are dereferenced when shading.  Like the reference
     // (kernel.cl:349) only the FIRST corner decides whether normals are used, so
     // when it has one the other two must be valid as well.
@@ -192,6 +267,7 @@ bool clpt_pack_scene(const kdnode *nodes, size_t n_nodes, const int *tri_indices
         out.root_min[a] = nodes[0].min.s[a];
         out.root_max[a] = nodes[0].max.s[a];
     }
+    timer.lap("normals check");
     // ---- start-node table ----
     // For a point p the kernel's descent takes child[1] iff p[axis] > plane.  Every
     // point of a cell [lo, hi] takes the same branch at a split when hi <= plane
@@ -258,6 +334,7 @@ bool clpt_pack_scene(const kdnode *nodes, size_t n_nodes, const int *tri_indices
             }
         }
     }
+    timer.lap("start table");
     out.n_nodes = n_packed;
     out.n_leaves = n_leaves;
     out.n_refs = (int)n_refs;

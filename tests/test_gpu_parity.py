@@ -471,3 +471,14 @@ def test_fails_loudly(clpt):
         p = subprocess.run([sys.executable, "-c", code % (str(root), body)], capture_output=True, text=True)
         assert p.returncode == 1, (body, p.returncode, p.stderr)
         assert needle in p.stderr, (body, p.stderr)
+    # inconsistent scenes are rejected on upload, before any kernel can dereference them
+    prep = ("from clpathtracer_b200 import scenes;s=cl.build_kd(*scenes.heightfield(6,True));"
+            "r=cl.Renderer(0);")
+    for corrupt, needle in [("s.nodes['c'][0,1]=10**6", "malformed"), ("s.tri_indices[3]=10**6", "tri_indices"),
+                            ("s.tris[5,0]=10**6", "missing vertex"), ("s.tris[0,1]=10**6", "normal"),
+                            ("s.nodes['type'][2]=7", "has type"),
+                            ("i=int((s.nodes['type']==1).argmax());s.nodes['c'][i,2]=10**6", "rope")]:
+        p = subprocess.run([sys.executable, "-c", code % (str(root), prep + corrupt + ";r.set_meshes(s)")],
+                           capture_output=True, text=True)
+        assert p.returncode == 1, (corrupt, p.returncode, p.stderr)
+        assert "invalid scene" in p.stderr and needle in p.stderr, (corrupt, p.stderr)
