@@ -194,6 +194,23 @@ __device__ __forceinline__ bool hit_is_final(int ref, float tmin, float min_hit)
     return ref >= 0 && (double)tmin + 0.001 > (double)min_hit;
 }
 
+// Step across the exit face of a leaf: p1 = orig + tmax*dir (:385), follow the rope
+// (:384); true when the ray leaves the scene or exhausts its rope-hop budget.
+template <bool COUNT>
+__device__ __forceinline__ bool leave_leaf(const uint2 *__restrict__ nodes, const float4 *L, int far, V3 o, V3 d,
+                                           float tmax, int max_visits, V3 &p1, uint2 &n, int &visits, Counters &cn) {
+    p1 = vadd(o, vscale(d, tmax));
+    const int next = __ldg(reinterpret_cast<const int *>(L + 2) + far);
+    if (next == -1) return true;
+    if (++visits >= max_visits) {
+        if (COUNT) cn.capped++;
+        return true;
+    }
+    // ropes <= -2 name a leaf record directly: its node word is implied, nothing to fetch
+    n = next >= 0 ? __ldg(nodes + next) : make_uint2((unsigned)(-2 - next), CLPT_LEAF_WORD);
+    return false;
+}
+
 // Traversal of one ray to completion.
 template <bool COUNT>
 __device__ __forceinline__ Hit closest_hit(const ClptScene &S, V3 o, V3 d, int max_visits,
@@ -219,24 +236,18 @@ __device__ __forceinline__ Hit closest_hit(const ClptScene &S, V3 o, V3 d, int m
         if (COUNT) cn.leaves++;
         const float4 *L = S.leaves + 4 * (size_t)n.x;
         const float4 lmin = __ldg(L), lmax = __ldg(L + 1);
-        // The exit depends only on the leaf box and the ray, so it is evaluated BEFORE
-        // the triangle run: three values stay live across the run instead of eight.
+        // The exit depends only on the leaf box and the ray, so it is evaluated BEFORE the
+        // triangle run: two values stay live across the run instead of the box.  (Also
+        // requesting the rope and the neighbour's node word here, to overlap them with the
+        // run, was measured: three more live values spill at 32 registers and the L1 data
+        // pipe is the busiest unit, so it costs 4%.  A separate inner loop for empty leaves
+        // was measured too: -8%.  profiles/r01_experiments.json)
         int far;
         leaf_exit(lmin, lmax, o, inv, tmax, far);
-        // The neighbour across the exit face and its node word are requested now, so
-        // the two dependent loads overlap the triangle run instead of following it.
-        const int next = __ldg(reinterpret_cast<const int *>(L + 2) + far);
-        uint2 n_next = make_uint2((unsigned)(-2 - next), CLPT_LEAF_WORD); // neighbour is a leaf: its word is implied
-        if (next >= 0) n_next = __ldg(nodes + next);
         triangle_run<COUNT>(S.tri, __float_as_int(lmin.w), __float_as_int(lmax.w), o, d, h.ref, min_hit, cn);
+        // (the box is re-read from L1 rather than kept live across the run)
         if (h.ref >= 0 && hit_is_final(h.ref, leaf_entry(__ldg(L), __ldg(L + 1), o, inv), min_hit)) break;
-        p1 = vadd(o, vscale(d, tmax)); // :385
-        if (next == -1) break;
-        if (++visits >= max_visits) {
-            if (COUNT) cn.capped++;
-            break;
-        }
-        n = n_next;
+        if (leave_leaf<COUNT>(nodes, L, far, o, d, tmax, max_visits, p1, n, visits, cn)) break;
     }
     h.t = min_hit;
     return h;

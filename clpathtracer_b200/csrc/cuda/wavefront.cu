@@ -165,20 +165,9 @@ wf_trace(const __grid_constant__ ClptScene S, const float4 *__restrict__ qa, con
             float tmax;
             int far;
             leaf_exit(lmin, lmax, o, inv, tmax, far);
-            const int next = __ldg(reinterpret_cast<const int *>(L + 2) + far);
-            uint2 n_next = make_uint2((unsigned)(-2 - next), CLPT_LEAF_WORD);
-            if (next >= 0) n_next = __ldg(nodes + next);
             triangle_run<COUNT>(S.tri, __float_as_int(lmin.w), __float_as_int(lmax.w), o, d, ref, min_hit, cn);
             bool done = ref >= 0 && hit_is_final(ref, leaf_entry(__ldg(L), __ldg(L + 1), o, inv), min_hit);
-            if (!done) {
-                p1 = vadd(o, vscale(d, tmax));
-                done = next == -1;
-                if (!done && ++visits >= max_visits) {
-                    if (COUNT) cn.capped++;
-                    done = true;
-                }
-                n = n_next;
-            }
+            if (!done) done = leave_leaf<COUNT>(nodes, L, far, o, d, tmax, max_visits, p1, n, visits, cn);
             if (done) {
                 hits[slot] = make_int2(ref, __float_as_int(min_hit));
                 slot = -1;
