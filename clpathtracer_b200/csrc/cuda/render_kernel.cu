@@ -121,7 +121,13 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
     const int spp = F.spp < 1 ? 1 : F.spp;
     const int group_base = lane & ~(s_lanes - 1);
     Counters cn = { 0, 0, 0, 0, 0, 0 };
-    V3 acc = mk(0.0f, 0.0f, 0.0f);
+    // Ordered per-pixel sum.  The colours of a round are staged in shared memory and
+    // summed in ascending sample order by one lane per channel (lane c of the pixel's
+    // group sums channel c; with fewer than 4 lanes per pixel, lane 0 sums all three).
+    // Same additions in the same order as a serial loop over the samples.
+    __shared__ float stage[8][3][33]; // [warp][channel][lane], rows padded against bank conflicts
+    const bool per_channel = s_lanes >= 4;
+    V3 acc = mk(0.0f, 0.0f, 0.0f); // per_channel: only .x is used, for channel `sslot`
     for (int base = 0; base < spp; base += s_lanes) {
         const int s = base + sslot;
         V3 colour = mk(0.0f, 0.0f, 0.0f);
@@ -129,14 +135,29 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
             colour = trace_sample<MODE, COUNT>(S, F, x, y, pixel, F.sample_base + (unsigned)s,
                                                s == 0 && F.aov_prim != nullptr, cn);
         }
-        // ordered sum over the samples of this round (every lane of the group
-        // computes the same running sum)
-        for (int j = 0; j < s_lanes; j++) {
-            const float cx = __shfl_sync(0xffffffffu, colour.x, group_base + j);
-            const float cy = __shfl_sync(0xffffffffu, colour.y, group_base + j);
-            const float cz = __shfl_sync(0xffffffffu, colour.z, group_base + j);
-            if (base + j < spp) acc = vadd(acc, mk(cx, cy, cz));
+        stage[warp][0][lane] = colour.x;
+        stage[warp][1][lane] = colour.y;
+        stage[warp][2][lane] = colour.z;
+        __syncwarp();
+        const int in_round = min(s_lanes, spp - base);
+        if (per_channel) {
+            if (sslot < 3) {
+                const float *src = &stage[warp][sslot][group_base];
+                for (int j = 0; j < in_round; j++) acc.x = fadd(acc.x, src[j]);
+            }
+        } else if (sslot == 0) {
+            for (int j = 0; j < in_round; j++) {
+                acc = vadd(acc, mk(stage[warp][0][group_base + j], stage[warp][1][group_base + j],
+                                   stage[warp][2][group_base + j]));
+            }
         }
+        __syncwarp();
+    }
+    if (per_channel) { // bring the three channel sums to the group's first lane
+        const float r = __shfl_sync(0xffffffffu, acc.x, group_base);
+        const float g = __shfl_sync(0xffffffffu, acc.x, group_base + 1);
+        const float b = __shfl_sync(0xffffffffu, acc.x, group_base + 2);
+        acc = mk(r, g, b);
     }
     if (valid && sslot == 0) store_pixel(F, x, ly, acc, spp);
     if (COUNT) {
