@@ -12,12 +12,6 @@
 #ifndef CLPT_EXPERIMENT_FMA
 #define CLPT_EXPERIMENT_FMA 0
 #endif
-#ifndef CLPT_RELOAD_E2
-#define CLPT_RELOAD_E2 1
-#endif
-#ifndef CLPT_RELOAD_E1
-#define CLPT_RELOAD_E1 1
-#endif
 #ifndef CLPT_START_LUT
 #define CLPT_START_LUT 1
 #endif
@@ -183,25 +177,19 @@ __device__ __forceinline__ void triangle_run(const float4 *__restrict__ tri, int
         const V3 tvec = vsub(o, xyz(a));
         const float u = fmul(vdot(tvec, pvec), idet);
         if (u < 0.0f || u > 1.0f) continue;
-#if CLPT_RELOAD_E1
-        const float4 *again1 = tri + 3 * (size_t)i + 1; // same trick for e1, needed only past the u test
+        // e1 and e2 are NOT kept live from the determinant to where they are next needed:
+        // the few candidates that get this far fetch them again (L1 hits).  At 32 registers
+        // the test otherwise fills the file and the ray constants spill around it -- spill
+        // traffic was half of the L1 data pipe's load, the busiest unit (profiles/).  The
+        // laundered pointers stop the compiler from merging the loads back together.
+        const float4 *again1 = tri + 3 * (size_t)i + 1;
         asm volatile("" : "+l"(again1));
         const V3 qvec = vcross(tvec, xyz(__ldg(again1)));
-#else
-        const V3 qvec = vcross(tvec, e1);
-#endif
         const float v = fmul(vdot(d, qvec), idet);
         if (v < 0.0f || fadd(u, v) > 1.0f) continue;
-#if CLPT_RELOAD_E2
-        // e2 is not kept live through the u/v tests: the few candidates that get here
-        // fetch it again (an L1 hit).  The laundered pointer stops the compiler from
-        // merging this load with the first one, which would keep the registers busy.
-        const float4 *again = tri + 3 * (size_t)i + 2;
-        asm volatile("" : "+l"(again));
-        const float t = fmul(vdot(xyz(__ldg(again)), qvec), idet);
-#else
-        const float t = fmul(vdot(e2, qvec), idet);
-#endif
+        const float4 *again2 = tri + 3 * (size_t)i + 2;
+        asm volatile("" : "+l"(again2));
+        const float t = fmul(vdot(xyz(__ldg(again2)), qvec), idet);
         if (!(t > 0.0f)) continue;
         if (ref < 0 || t <= min_hit) { // the later triangle wins ties (:344)
             min_hit = t;

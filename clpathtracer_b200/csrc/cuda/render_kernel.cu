@@ -3,7 +3,7 @@
 // One launch = one frame (or one rank's row tiles of it): per pixel sample,
 // camera ray generation -> stackless kd-tree traversal with ropes ->
 // Moller-Trumbore over the leaf's contiguous triangle run -> shading ->
-// in-register accumulation over the samples -> one float4 store.
+// ordered accumulation over the samples -> one float4 store.
 //
 // What it computes is what the reference kernel computes (src/kernel.cl:296-473,
 // see oracle/oracle_kernel.c for the restatement it is checked against); how
