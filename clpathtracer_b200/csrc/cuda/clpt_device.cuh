@@ -70,12 +70,14 @@ struct ClptFrame {
     float *aov_t;
     float2 *aov_uv;
     unsigned long long *counters; // 6 counters, may be null
+    unsigned int *work_counter;   // warp-tile claim counter of the persistent render kernel
+    int blocks_x, n_warp_tiles;   // filled in by clpt_launch_render
 };
 
 enum { CLPT_F_JITTER = 1, CLPT_F_ACCUMULATE = 2, CLPT_F_COUNTERS = 4 };
 
 // render_kernel.cu
-void clpt_launch_render(const ClptScene &scene, const ClptFrame &frame, cudaStream_t stream);
+void clpt_launch_render(const ClptScene &scene, const ClptFrame &frame, int sm_count, cudaStream_t stream);
 void clpt_launch_deinterleave(const float4 *gathered, float4 *image, int width, int height,
                               int nranks, int tile_rows, int slab_rows, cudaStream_t stream);
 void clpt_launch_fill(float4 *dst, size_t n, float value, cudaStream_t stream);

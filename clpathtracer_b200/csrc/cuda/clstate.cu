@@ -149,6 +149,7 @@ struct {
     DevBuf<float> aov_t;
     DevBuf<float2> aov_uv;
     DevBuf<unsigned long long> counters;
+    DevBuf<unsigned int> work_counter;
     unsigned long long host_counters[6] = { 0 };
     float last_kernel_ms = 0;
     int last_launches = 0;
@@ -323,6 +324,9 @@ void clpt_state_launch_frame(int width, int height) {
     F.aov_t = St.aov ? St.aov_t.ptr : nullptr;
     F.aov_uv = St.aov ? St.aov_uv.ptr : nullptr;
     F.counters = nullptr;
+    if (!St.work_counter.ptr) St.work_counter.resize(1);
+    F.work_counter = St.work_counter.ptr;
+    F.blocks_x = F.n_warp_tiles = 0;
     if (St.flags & CLPT_FLAG_COUNTERS) {
         if (!St.counters.ptr) St.counters.resize(6);
         CU(cudaMemsetAsync(St.counters.ptr, 0, 6 * sizeof(unsigned long long), St.stream));
@@ -356,7 +360,7 @@ void clpt_state_launch_frame(int width, int height) {
         if (n < 0) FATAL("wavefront workspace too small");
         St.last_launches += n;
     } else {
-        clpt_launch_render(St.scene, F, St.stream);
+        clpt_launch_render(St.scene, F, St.prop.multiProcessorCount, St.stream);
         St.last_launches++;
     }
     CU(cudaGetLastError());
@@ -453,6 +457,7 @@ void CLTerminate(void) {
     St.aov_t.release();
     St.aov_uv.release();
     St.counters.release();
+    St.work_counter.release();
     St.l2_flush.release();
     St.wf_workspace.release();
     St.wf_max_paths = 0;

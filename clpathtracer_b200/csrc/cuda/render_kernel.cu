@@ -112,12 +112,6 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
     int tw, th;
     warp_tile_dims(5 - log2_s, tw, th);
     const int pslot = lane >> log2_s, sslot = lane & (s_lanes - 1);
-    const int x = (blockIdx.x * 4 + (warp & 3)) * tw + (pslot & (tw - 1));
-    // row within this rank's slab
-    const int ly = (blockIdx.y * 2 + (warp >> 2)) * th + pslot / tw;
-    const int y = slab_row_to_image_row(F, ly);
-    const bool valid = x < F.width && y < F.height && ly < F.local_rows;
-    const unsigned pixel = (unsigned)(y * F.width + x);
     const int spp = F.spp < 1 ? 1 : F.spp;
     const int group_base = lane & ~(s_lanes - 1);
     Counters cn = { 0, 0, 0, 0, 0, 0 };
@@ -127,39 +121,60 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
     // Same additions in the same order as a serial loop over the samples.
     __shared__ float stage[8][3][33]; // [warp][channel][lane], rows padded against bank conflicts
     const bool per_channel = s_lanes >= 4;
-    V3 acc = mk(0.0f, 0.0f, 0.0f); // per_channel: only .x is used, for channel `sslot`
-    for (int base = 0; base < spp; base += s_lanes) {
-        const int s = base + sslot;
-        V3 colour = mk(0.0f, 0.0f, 0.0f);
-        if (valid && s < spp) {
-            colour = trace_sample<MODE, COUNT>(S, F, x, y, pixel, F.sample_base + (unsigned)s,
-                                               s == 0 && F.aov_prim != nullptr, cn);
-        }
-        stage[warp][0][lane] = colour.x;
-        stage[warp][1][lane] = colour.y;
-        stage[warp][2][lane] = colour.z;
-        __syncwarp();
-        const int in_round = min(s_lanes, spp - base);
-        if (per_channel) {
-            if (sslot < 3) {
-                const float *src = &stage[warp][sslot][group_base];
-                for (int j = 0; j < in_round; j++) acc.x = fadd(acc.x, src[j]);
+    // Persistent warps: the grid only fills the machine; every warp claims warp tiles
+    // from a global counter until none are left.  Blocks cost anything from nothing
+    // (sky) to hundreds of microseconds (grazing ground), and with one tile per warp
+    // fixed at launch the last heavy blocks left most SMs idle at the end of a frame
+    // (40% idle on a 4 ms frame).  Tile t = ((by * tiles_x + bx) * 8 + w): the same
+    // 4 x 2 arrangement of warp tiles as a block of the static mapping, so
+    // consecutive claims are neighbours on screen.
+    const unsigned bx_count = (unsigned)F.blocks_x, n_tiles = (unsigned)F.n_warp_tiles;
+    for (;;) {
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(F.work_counter, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= n_tiles) break;
+        const unsigned w = t & 7u, b = t >> 3;
+        const int bx = (int)(b % bx_count), by = (int)(b / bx_count);
+        const int x = (bx * 4 + (int)(w & 3u)) * tw + (pslot & (tw - 1));
+        const int ly = (by * 2 + (int)(w >> 2)) * th + pslot / tw; // row within this rank's slab
+        const int y = slab_row_to_image_row(F, ly);
+        const bool valid = x < F.width && y < F.height && ly < F.local_rows;
+        const unsigned pixel = (unsigned)(y * F.width + x);
+        V3 acc = mk(0.0f, 0.0f, 0.0f); // per_channel: only .x is used, for channel `sslot`
+        for (int base = 0; base < spp; base += s_lanes) {
+            const int s = base + sslot;
+            V3 colour = mk(0.0f, 0.0f, 0.0f);
+            if (valid && s < spp) {
+                colour = trace_sample<MODE, COUNT>(S, F, x, y, pixel, F.sample_base + (unsigned)s,
+                                                   s == 0 && F.aov_prim != nullptr, cn);
             }
-        } else if (sslot == 0) {
-            for (int j = 0; j < in_round; j++) {
-                acc = vadd(acc, mk(stage[warp][0][group_base + j], stage[warp][1][group_base + j],
-                                   stage[warp][2][group_base + j]));
+            stage[warp][0][lane] = colour.x;
+            stage[warp][1][lane] = colour.y;
+            stage[warp][2][lane] = colour.z;
+            __syncwarp();
+            const int in_round = min(s_lanes, spp - base);
+            if (per_channel) {
+                if (sslot < 3) {
+                    const float *src = &stage[warp][sslot][group_base];
+                    for (int j = 0; j < in_round; j++) acc.x = fadd(acc.x, src[j]);
+                }
+            } else if (sslot == 0) {
+                for (int j = 0; j < in_round; j++) {
+                    acc = vadd(acc, mk(stage[warp][0][group_base + j], stage[warp][1][group_base + j],
+                                       stage[warp][2][group_base + j]));
+                }
             }
+            __syncwarp();
         }
-        __syncwarp();
+        if (per_channel) { // bring the three channel sums to the group's first lane
+            const float r = __shfl_sync(0xffffffffu, acc.x, group_base);
+            const float g = __shfl_sync(0xffffffffu, acc.x, group_base + 1);
+            const float bl = __shfl_sync(0xffffffffu, acc.x, group_base + 2);
+            acc = mk(r, g, bl);
+        }
+        if (valid && sslot == 0) store_pixel(F, x, ly, acc, spp);
     }
-    if (per_channel) { // bring the three channel sums to the group's first lane
-        const float r = __shfl_sync(0xffffffffu, acc.x, group_base);
-        const float g = __shfl_sync(0xffffffffu, acc.x, group_base + 1);
-        const float b = __shfl_sync(0xffffffffu, acc.x, group_base + 2);
-        acc = mk(r, g, b);
-    }
-    if (valid && sslot == 0) store_pixel(F, x, ly, acc, spp);
     if (COUNT) {
         unsigned v[6] = { cn.rays, cn.splits, cn.leaves, cn.tris, cn.shade_vn, cn.capped };
 #pragma unroll
@@ -202,7 +217,7 @@ __global__ void normalise_kernel(const float4 *__restrict__ src, float4 *__restr
 }
 
 template <int MODE>
-void launch_mode(const ClptScene &scene, const ClptFrame &frame, dim3 grid, cudaStream_t stream) {
+void launch_mode(const ClptScene &scene, const ClptFrame &frame, unsigned grid, cudaStream_t stream) {
     if (frame.flags & CLPT_F_COUNTERS) {
         render_kernel<MODE, true><<<grid, 256, 0, stream>>>(scene, frame);
     } else {
@@ -212,12 +227,20 @@ void launch_mode(const ClptScene &scene, const ClptFrame &frame, dim3 grid, cuda
 
 } // namespace
 
-void clpt_launch_render(const ClptScene &scene, const ClptFrame &frame, cudaStream_t stream) {
+void clpt_launch_render(const ClptScene &scene, const ClptFrame &frame_in, int sm_count, cudaStream_t stream) {
+    ClptFrame frame = frame_in;
     int tw, th;
     warp_tile_dims(5 - frame.log2_sample_lanes, tw, th);
     const int block_w = 4 * tw, block_h = 2 * th;
-    dim3 grid((frame.width + block_w - 1) / block_w, (frame.local_rows + block_h - 1) / block_h);
-    if (grid.x == 0 || grid.y == 0) return;
+    const unsigned bx = (unsigned)((frame.width + block_w - 1) / block_w);
+    const unsigned by = (unsigned)((frame.local_rows + block_h - 1) / block_h);
+    if (bx == 0 || by == 0) return;
+    frame.blocks_x = (int)bx;
+    frame.n_warp_tiles = (int)(bx * by * 8u);
+    // persistent grid: enough blocks to fill every SM, never more than there are tiles
+    unsigned grid = (unsigned)sm_count * CLPT_MIN_BLOCKS;
+    if (grid > bx * by) grid = bx * by;
+    cudaMemsetAsync(frame.work_counter, 0, sizeof(unsigned), stream);
     switch (frame.mode) {
     case 0: launch_mode<0>(scene, frame, grid, stream); break;
     case 1: launch_mode<1>(scene, frame, grid, stream); break;
