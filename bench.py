@@ -51,7 +51,7 @@ def parse_args():
                     help="ref: the reference's heuristic at --tree-depth; sah: build_kd_sah (extension)")
     ap.add_argument("--sah-ci", type=float, default=1.0)
     ap.add_argument("--sah-bonus", type=float, default=0.9)
-    ap.add_argument("--sah-bins", type=int, default=32)
+    ap.add_argument("--sah-bins", type=int, default=0, help="0: exact sweep over all triangle bounds")
     ap.add_argument("--mode", default="mirror", choices=["mirror", "path"],
                     help="mirror: the reference's bounce (mode B); path: diffuse BSDF extension (mode C)")
     ap.add_argument("--engine", type=int, default=int(os.environ.get("CLPT_ENGINE", "0")),

@@ -221,7 +221,7 @@ def build_kd(verts: np.ndarray, corners: np.ndarray, norms: np.ndarray | None = 
 
 def build_kd_sah(verts: np.ndarray, corners: np.ndarray, norms: np.ndarray | None = None,
                  max_depth: int | None = None, nbins: int = 32, traversal_cost: float = 1.0,
-                 intersect_cost: float = 1.5, empty_bonus: float = 0.8, path: str | None = None) -> Scene:
+                 intersect_cost: float = 1.0, empty_bonus: float = 0.9, path: str | None = None) -> Scene:
     """SAH kd-tree (extension, clpt_host.h build_kd_sah): same wire format and ropes."""
     L = lib()
     v4 = _as_vec4(verts)

@@ -99,10 +99,11 @@ kd build_kd(cl_int3 *tris, Vector3 *verts, Vector3 *norms, const char *path);
 kd build_kd_ex(cl_int3 *tris, Vector3 *verts, Vector3 *norms, const char *path,
                int depth, int nbins);
 /* Extension (no reference counterpart): standard surface-area heuristic with a
- * leaf-cost termination, `nbins` uniform planes per axis in large cells and all
- * triangle bounds in small ones.  Same wire format, same ropes.  Suggested:
- * max_depth 8 + 1.3*log2(triangles), nbins 32, traversal_cost 1, intersect_cost
- * 1.5, empty_bonus 0.8. */
+ * leaf-cost termination; candidate planes are all triangle bounds (nbins <= 0),
+ * or `nbins` uniform planes per axis in cells of more than 48 triangles
+ * (nbins > 0).  Same wire format; ropes pushed down further than the reference
+ * does.  Suggested: max_depth 8 + 1.3*log2(triangles), nbins 0, traversal_cost 1,
+ * intersect_cost 1, empty_bonus 0.9. */
 kd build_kd_sah(cl_int3 *tris, Vector3 *verts, Vector3 *norms, const char *path,
                 int max_depth, int nbins, float traversal_cost, float intersect_cost,
                 float empty_bonus);

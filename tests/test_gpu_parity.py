@@ -74,13 +74,15 @@ def test_deterministic_modes_bit_exact(clpt, oracle, renderer, scene_cache, name
     assert (prim >= 0).mean() > (0.01 if name.startswith('soup') else 0.05)  # the camera sees the scene
 
 
-@pytest.mark.parametrize("name,camera,w,h,mode,depth", [("hf224", "canonical", 480, 270, 1, 5),
-                                                         ("cornell", "cornell", 320, 240, 1, 4),
-                                                         ("soup3000", "cornell", 256, 256, 1, 4),
-                                                         ("hf22n", "reference", 333, 197, 0, 2)])
-def test_sah_trees_bit_exact(clpt, oracle, renderer, scene_cache, name, camera, w, h, mode, depth):
-    """Trees from the SAH builder (extension) go through the same traversal."""
-    scene, _ = scene_cache(name, sah=True)
+@pytest.mark.parametrize("name,camera,w,h,mode,depth,sah", [("hf224", "canonical", 480, 270, 1, 5, True),
+                                                             ("cornell", "cornell", 320, 240, 1, 4, True),
+                                                             ("soup3000", "cornell", 256, 256, 1, 4, True),
+                                                             ("hf22n", "reference", 333, 197, 0, 2, True),
+                                                             ("hf224", "canonical", 480, 270, 1, 5, "exact"),
+                                                             ("soup3000", "cornell", 256, 256, 1, 4, "exact")])
+def test_sah_trees_bit_exact(clpt, oracle, renderer, scene_cache, name, camera, w, h, mode, depth, sah):
+    """Trees from the SAH builder (extension; binned and exact-sweep) go through the same traversal."""
+    scene, _ = scene_cache(name, sah=sah)
     cam = _cam(clpt, camera, h)
     img, prim, t, uv = _render_gpu(renderer, scene, cam, w, h, mode=mode, depth=depth)
     ref = oracle.render(scene, cam, w, h, mode=mode, depth=depth)

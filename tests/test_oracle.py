@@ -75,7 +75,11 @@ def _brute_force(scene, cam, w, h):
 
 @pytest.mark.parametrize("name,camera,sah", [("hf22", "canonical", False), ("cornell", "cornell", False),
                                              ("soup500", "cornell", False), ("hf22", "canonical", True),
-                                             ("cornell", "cornell", True), ("soup500", "cornell", True)])
+                                             ("cornell", "cornell", True), ("soup500", "cornell", True),
+                                             # exact-sweep SAH puts planes ON mesh grid lines; hf21 keeps the
+                                             # centred camera's x = 0 pixel column off them (kd_build.c, partition)
+                                             ("hf21", "canonical", "exact"), ("cornell", "cornell", "exact"),
+                                             ("soup500", "cornell", "exact")])
 def test_traversal_against_brute_force(clpt, oracle, scene_cache, name, camera, sah):
     """Rope traversal must find the globally closest front-facing hit.  The
     reference traversal is not watertight (split-plane
