@@ -344,7 +344,72 @@ typedef struct sah_params {
     int max_depth, nbins;
     float ct, ci, empty_bonus;
     int exact_below; /* cells with at most this many triangles evaluate every triangle bound */
+    int clip;        /* re-derive a straddler's bounds from the triangle clipped to each child */
+    const cl_int3 *corners;
+    const Vector3 *verts;
 } sah_params;
+
+/* Bounds of triangle `id` clipped to the box [cmin, cmax] ("perfect splits", Wald &
+ * Havran 2006): Sutherland-Hodgman in double against the six faces, then the polygon's
+ * extent, widened outward by one float ulp and intersected with the bounds handed in.
+ * A triangle's box overlaps far more cells than the triangle does when it is long and
+ * thin; tight bounds put the next candidate planes where the surface really is.
+ * Returns 0 (bounds untouched) if nothing is left of the polygon, which can only be a
+ * rounding artefact because every reference in a cell came from a clipped parent. */
+static int
+clip_bounds(const sah_params *P, int id, const float *cmin, const float *cmax, float lo[3], float hi[3]) {
+    double a[10][3], b[10][3];
+    double (*src)[3] = a, (*dst)[3] = b;
+    int np = 3;
+    for (int k = 0; k < 3; k++) {
+        const Vector3 v = P->verts[P->corners[3 * id + k].s[0]];
+        for (int c = 0; c < 3; c++) {
+            src[k][c] = v.s[c];
+        }
+    }
+    for (int axis = 0; axis < 3 && np > 0; axis++) {
+        for (int side = 0; side < 2 && np > 0; side++) {
+            const double plane = side ? cmax[axis] : cmin[axis];
+            int nq = 0;
+            for (int k = 0; k < np; k++) {
+                const double *p = src[k], *q = src[(k + 1) % np];
+                const int pin = side ? p[axis] <= plane : p[axis] >= plane;
+                const int qin = side ? q[axis] <= plane : q[axis] >= plane;
+                if (pin) {
+                    memcpy(dst[nq++], p, sizeof(double) * 3);
+                }
+                if (pin != qin) {
+                    const double t = (plane - p[axis]) / (q[axis] - p[axis]);
+                    for (int c = 0; c < 3; c++) {
+                        dst[nq][c] = p[c] + t * (q[c] - p[c]);
+                    }
+                    dst[nq++][axis] = plane;
+                }
+            }
+            double (*tmp)[3] = src;
+            src = dst;
+            dst = tmp;
+            np = nq;
+        }
+    }
+    if (np == 0) {
+        return 0;
+    }
+    for (int c = 0; c < 3; c++) {
+        double mn = src[0][c], mx = src[0][c];
+        for (int k = 1; k < np; k++) {
+            mn = src[k][c] < mn ? src[k][c] : mn;
+            mx = src[k][c] > mx ? src[k][c] : mx;
+        }
+        float fl = nextafterf((float)mn, -INFINITY), fh = nextafterf((float)mx, INFINITY);
+        if (fl > lo[c]) lo[c] = fl;
+        if (fh < hi[c]) hi[c] = fh;
+        if (lo[c] > hi[c]) { /* cannot happen for a real overlap; stay safe */
+            lo[c] = hi[c] = (float)(0.5 * (mn + mx));
+        }
+    }
+    return 1;
+}
 
 static int
 cmp_float(const void *a, const void *b) {
@@ -524,15 +589,34 @@ build_cell_sah(tri_set s, const float *bmin, const float *bmax, int depth, const
      * 2x the triangle tests (the copies are carried down every level). */
     tri_set L = tri_set_alloc(n), R = tri_set_alloc(n);
     const float *lo = s.lo[best_axis], *hi = s.hi[best_axis];
+    float lmax[3], rmin[3];
+    memcpy(lmax, bmax, sizeof(lmax));
+    memcpy(rmin, bmin, sizeof(rmin));
+    lmax[best_axis] = rmin[best_axis] = best_v;
     for (int t = 0; t < n; t++) {
+        const int straddles = lo[t] < best_v && hi[t] > best_v;
         if (lo[t] < best_v || (lo[t] == hi[t] && lo[t] == best_v)) {
             tri_set_push(&L, &s, t);
             /* clip the handed-down bound to the child */
             if (L.hi[best_axis][L.n - 1] > best_v) L.hi[best_axis][L.n - 1] = best_v;
+            if (straddles && P->clip) {
+                float b0[3], b1[3];
+                for (int a = 0; a < 3; a++) { b0[a] = L.lo[a][L.n - 1]; b1[a] = L.hi[a][L.n - 1]; }
+                if (clip_bounds(P, s.id[t], bmin, lmax, b0, b1)) {
+                    for (int a = 0; a < 3; a++) { L.lo[a][L.n - 1] = b0[a]; L.hi[a][L.n - 1] = b1[a]; }
+                }
+            }
         }
         if (hi[t] > best_v) {
             tri_set_push(&R, &s, t);
             if (R.lo[best_axis][R.n - 1] < best_v) R.lo[best_axis][R.n - 1] = best_v;
+            if (straddles && P->clip) {
+                float b0[3], b1[3];
+                for (int a = 0; a < 3; a++) { b0[a] = R.lo[a][R.n - 1]; b1[a] = R.hi[a][R.n - 1]; }
+                if (clip_bounds(P, s.id[t], rmin, bmax, b0, b1)) {
+                    for (int a = 0; a < 3; a++) { R.lo[a][R.n - 1] = b0[a]; R.hi[a][R.n - 1] = b1[a]; }
+                }
+            }
         }
     }
     /* a split that separates nothing and removes no volume would recurse forever */
@@ -545,10 +629,6 @@ build_cell_sah(tri_set s, const float *bmin, const float *bmax, int depth, const
     }
     int big = n >= 1024;
     tri_set_free(&s);
-    float lmax[3], rmin[3];
-    memcpy(lmax, bmax, sizeof(lmax));
-    memcpy(rmin, bmin, sizeof(rmin));
-    lmax[best_axis] = rmin[best_axis] = best_v;
     out = arena_alloc(sizeof(*out));
     memcpy(out->bmin, bmin, sizeof(out->bmin));
     memcpy(out->bmax, bmax, sizeof(out->bmax));
@@ -860,7 +940,9 @@ build_kd_sah(cl_int3 *tris, Vector3 *verts, Vector3 *norms, const char *path,
              float empty_bonus) {
     /* nbins <= 0: every triangle bound is a candidate at every cell size (sorted sweep) */
     sah_params P = { max_depth, nbins, traversal_cost, intersect_cost, empty_bonus,
-                     nbins > 0 ? SAH_EXACT_BELOW : 0x7fffffff };
+                     nbins > 0 ? SAH_EXACT_BELOW : 0x7fffffff, 1, tris, verts };
+    const char *e = getenv("CLPT_SAH_CLIP");
+    if (e) P.clip = atoi(e);
     return build_tree(tris, verts, norms, path, 0, 0, &P);
 }
 
