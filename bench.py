@@ -90,7 +90,9 @@ def workload_config(a):
         "render_mode": a.mode, "kd_builder": ("reference heuristic (src/kd_tree.c:95-200) at depth %d, 25 bins" % a.tree_depth) if a.builder == "ref"
                       else "build_kd_sah ci=%g bonus=%g bins=%d" % (a.sah_ci, a.sah_bonus, a.sah_bins),
         "mode": "mirror (src/kernel.cl:399-417 enabled)",
-        "sharding": f"row tiles of {a.tile_rows} rows, round-robin over ranks, scene replicated, NCCL all-gather",
+        "sharding": f"row tiles of {a.tile_rows} rows, round-robin over ranks, scene replicated; frame assembled by "
+                    + ("the render kernel storing into peer-mapped frames (NVLink), two one-word barriers per frame"
+                       if getattr(a, "direct_placement", 1) else "NCCL all-gather + de-interleave"),
         "l2": "flushed between timed frames (CLFlushL2, 256 MiB overwrite, outside the timed events)",
     }
 
@@ -374,6 +376,7 @@ def main():
         raw = idbuf.cpu().numpy().copy()
         L.CLDistInit(rank, world, raw.ctypes.data, a.tile_rows)
     r.create_image(a.width, a.height)
+    a.direct_placement = int(L.CLDistDirectPlacement()) if world > 1 else 1
     flags = cl.FLAG_JITTER | (cl.FLAG_ACCUMULATE if a.progressive else 0)
 
     def barrier():

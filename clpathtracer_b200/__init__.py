@@ -116,7 +116,7 @@ def lib() -> C.CDLL:
         "CLGetCounters": (None, [vp]), "CLLastKernelMs": (f, []), "CLLastLaunchCount": (i, []),
         "CLEventRecord": (None, [i]), "CLEventElapsedMs": (f, [i, i]), "CLFlushL2": (None, []),
         "CLDistGetUniqueId": (None, [vp]), "CLDistInit": (None, [i, i, vp, i]),
-        "CLDistShutdown": (None, []), "CLSetTileShard": (None, [i, i, i]),
+        "CLDistShutdown": (None, []), "CLDistDirectPlacement": (i, []), "CLSetTileShard": (None, [i, i, i]),
         "CLDeviceName": (C.c_char_p, []), "CLDeviceSMCount": (i, []),
     }
     for name, (res, args) in sig.items():

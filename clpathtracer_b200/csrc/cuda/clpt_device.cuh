@@ -56,6 +56,8 @@ struct ClptScene {
     float lut_scale[3]; // cells per unit length
 };
 
+#define CLPT_MAX_PEERS 8
+
 struct ClptFrame {
     float cam[16]; // row-major inverse camera matrix
     int width, height;
@@ -66,6 +68,12 @@ struct ClptFrame {
     int rank, nranks, tile_rows; // row-tile sharding; nranks == 1 -> whole image
     int local_rows;              // rows this rank renders (slab height)
     float4 *target;              // slab (nranks > 1) or the image itself
+    // Direct placement across GPUs: when n_peer_images > 0, every finished pixel is also
+    // stored at its image position in each of these full-size frames -- this rank's own
+    // and, through peer mappings over NVLink, every other rank's -- so the frame is
+    // assembled by the render kernel itself and no gather pass follows it.
+    float4 *peer_image[CLPT_MAX_PEERS];
+    int n_peer_images;
     int *aov_prim;               // full-image indexed, may be null
     float *aov_t;
     float2 *aov_uv;

@@ -399,15 +399,20 @@ __device__ __forceinline__ int slab_row_to_image_row(const ClptFrame &F, int ly)
 // Final store of a pixel's ordered sample sum (shared by both engines).
 __device__ __forceinline__ void store_pixel(const ClptFrame &F, int x, int ly, V3 acc, int spp) {
     float4 *dst = F.target + (size_t)ly * F.width + x;
+    float4 out;
     if (F.flags & CLPT_F_ACCUMULATE) {
         const float4 prev = *dst;
-        *dst = make_float4(fadd(prev.x, acc.x), fadd(prev.y, acc.y), fadd(prev.z, acc.z),
-                           fadd(prev.w, (float)spp));
+        out = make_float4(fadd(prev.x, acc.x), fadd(prev.y, acc.y), fadd(prev.z, acc.z), fadd(prev.w, (float)spp));
     } else if (spp == 1) {
-        *dst = make_float4(acc.x, acc.y, acc.z, 1.0f);
+        out = make_float4(acc.x, acc.y, acc.z, 1.0f);
     } else {
         const float k = fdiv(1.0f, (float)spp);
-        *dst = make_float4(fmul(acc.x, k), fmul(acc.y, k), fmul(acc.z, k), 1.0f);
+        out = make_float4(fmul(acc.x, k), fmul(acc.y, k), fmul(acc.z, k), 1.0f);
+    }
+    *dst = out;
+    if (F.n_peer_images > 0) { // multi-GPU direct placement: 16-byte stores into every rank's frame
+        const size_t at = (size_t)slab_row_to_image_row(F, ly) * F.width + x;
+        for (int r = 0; r < F.n_peer_images; r++) F.peer_image[r][at] = out;
     }
 }
 

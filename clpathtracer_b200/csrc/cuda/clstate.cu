@@ -44,6 +44,8 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
@@ -68,6 +70,7 @@ void nccl_load() {
     g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))sym("ncclGetUniqueId");
     g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))sym("ncclCommInitRank");
     g_nccl.AllGather = (decltype(g_nccl.AllGather))sym("ncclAllGather");
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))sym("ncclAllReduce");
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))sym("ncclCommDestroy");
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))sym("ncclGetErrorString");
 }
@@ -161,6 +164,12 @@ struct {
 
     int rank = 0, nranks = 1, tile_rows = 8;
     ncclComm_t comm = nullptr;
+    int comm_ranks = 0;
+    // direct placement (peer-mapped frames), see p2p_setup
+    bool p2p = false;
+    float4 *peer_image[CLPT_MAX_PEERS] = {};
+    DevBuf<int> dist_word;           // operand of the barrier all-reduce
+    DevBuf<unsigned char> dist_xchg; // handle exchange staging
 } St;
 
 void require_init(const char *who) {
@@ -262,7 +271,123 @@ void release_host_kd() {
     St.owns_kd = false;
 }
 
+// ---- multi-GPU direct placement -----------------------------------------------
+// With a communicator the render kernel assembles the frame itself: every rank maps
+// every other rank's frame (CUDA IPC; the mapping enables peer access over NVLink) and
+// store_pixel writes each finished pixel into all of them.  What is left of the
+// collective is ordering: one barrier before a frame (every rank is done reading the
+// previous one) and one after it (every rank's pixels have landed).  The barrier is a
+// one-word all-reduce on the library's stream.  If the mapping cannot be made on some
+// rank ($CLPT_P2P=0 on all ranks, no IPC, more than CLPT_MAX_PEERS ranks) every rank
+// falls back to slab + ncclAllGather + de-interleave.
+
+void dist_word_ready() {
+    if (!St.dist_word.ptr) {
+        St.dist_word.resize(2);
+        CU(cudaMemsetAsync(St.dist_word.ptr, 0, 2 * sizeof(int), St.stream));
+    }
+}
+
+void dist_barrier() {
+    dist_word_ready();
+    NC(g_nccl.AllReduce(St.dist_word.ptr, St.dist_word.ptr + 1, 1, ncclInt, ncclSum, St.comm, St.stream));
+}
+
+int dist_min(int v) {
+    dist_word_ready();
+    int out = 0;
+    CU(cudaMemcpyAsync(St.dist_word.ptr, &v, sizeof(int), cudaMemcpyHostToDevice, St.stream));
+    NC(g_nccl.AllReduce(St.dist_word.ptr, St.dist_word.ptr + 1, 1, ncclInt, ncclMin, St.comm, St.stream));
+    CU(cudaMemcpyAsync(&out, St.dist_word.ptr + 1, sizeof(int), cudaMemcpyDeviceToHost, St.stream));
+    CU(cudaStreamSynchronize(St.stream));
+    CU(cudaMemsetAsync(St.dist_word.ptr, 0, 2 * sizeof(int), St.stream));
+    return out;
+}
+
+void p2p_close_mappings() {
+    for (int r = 0; r < CLPT_MAX_PEERS; r++) {
+        if (St.peer_image[r] && St.peer_image[r] != St.image.ptr) {
+            const cudaError_t e = cudaIpcCloseMemHandle(St.peer_image[r]);
+            if (e != cudaSuccess) {
+                fprintf(stderr, "rank %d: unmapping rank %d's frame: %s\n", St.rank, r, cudaGetErrorName(e));
+                (void)cudaGetLastError(); // not fatal, and must not surface at the next launch check
+            }
+        }
+        St.peer_image[r] = nullptr;
+    }
+}
+
+// Collective over the communicator.  Must run before a mapped frame is freed or resized
+// and before the communicator goes away: an exporter may not free what a peer still maps.
+void p2p_teardown() {
+    if (!St.p2p) return;
+    CU(cudaStreamSynchronize(St.stream));
+    p2p_close_mappings();
+    St.p2p = false;
+    if (St.comm) {
+        dist_barrier();
+        CU(cudaStreamSynchronize(St.stream));
+    }
+}
+
+// Collective over the communicator: exchange the frames' IPC handles and map the peers'.
+void p2p_setup() {
+    St.p2p = false;
+    if (!St.comm || St.nranks < 2 || St.nranks > CLPT_MAX_PEERS || St.nranks != St.comm_ranks || !St.image.ptr) return;
+    if (const char *e = getenv("CLPT_P2P")) {
+        if (atoi(e) == 0) return; // has to be set on every rank alike
+    }
+    struct Slot {
+        cudaIpcMemHandle_t handle;
+        int ok;
+        int pad[15];
+    };
+    static_assert(sizeof(Slot) == 128, "exchange slot is 128 bytes");
+    Slot mine;
+    memset(&mine, 0, sizeof(mine));
+    mine.ok = cudaIpcGetMemHandle(&mine.handle, St.image.ptr) == cudaSuccess ? 1 : 0;
+    if (!mine.ok) (void)cudaGetLastError();
+    const size_t n = (size_t)St.nranks;
+    St.dist_xchg.resize(sizeof(Slot) * (n + 1));
+    std::vector<Slot> all(n);
+    CU(cudaMemcpyAsync(St.dist_xchg.ptr, &mine, sizeof(Slot), cudaMemcpyHostToDevice, St.stream));
+    NC(g_nccl.AllGather(St.dist_xchg.ptr, St.dist_xchg.ptr + sizeof(Slot), sizeof(Slot), ncclChar, St.comm,
+                        St.stream));
+    CU(cudaMemcpyAsync(all.data(), St.dist_xchg.ptr + sizeof(Slot), sizeof(Slot) * n, cudaMemcpyDeviceToHost,
+                       St.stream));
+    CU(cudaStreamSynchronize(St.stream));
+    int ok = 1;
+    for (size_t r = 0; r < n; r++) ok &= all[r].ok;
+    for (size_t r = 0; ok && r < n; r++) {
+        if ((int)r == St.rank) {
+            St.peer_image[r] = St.image.ptr;
+            continue;
+        }
+        void *mapped = nullptr;
+        if (cudaIpcOpenMemHandle(&mapped, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            (void)cudaGetLastError();
+            ok = 0;
+        } else {
+            St.peer_image[r] = (float4 *)mapped;
+        }
+    }
+    ok = dist_min(ok);
+    if (!ok) {
+        p2p_close_mappings();
+        dist_barrier();
+        CU(cudaStreamSynchronize(St.stream));
+        if (St.rank == 0) fprintf(stderr, "CLDistInit: peer frames could not be mapped; using ncclAllGather\n");
+        return;
+    }
+    St.p2p = true;
+    St.gathered.release(); // only the all-gather path needs it
+    if (getenv("CLPT_VERBOSE") && St.rank == 0) {
+        fprintf(stderr, "CLDistInit: %d ranks, frames peer-mapped, direct placement\n", St.nranks);
+    }
+}
+
 void alloc_targets() {
+    p2p_teardown();
     const size_t px = (size_t)St.width * St.height;
     St.image.resize(px);
     clpt_launch_fill(St.image.ptr, px, 0.0f, St.stream);
@@ -286,6 +411,7 @@ void alloc_targets() {
     St.scratch.release();
     St.sample_base = 0;
     CU(cudaStreamSynchronize(St.stream));
+    p2p_setup();
 }
 
 } // namespace
@@ -327,6 +453,9 @@ void clpt_state_launch_frame(int width, int height) {
     if (!St.work_counter.ptr) St.work_counter.resize(1);
     F.work_counter = St.work_counter.ptr;
     F.blocks_x = F.n_warp_tiles = 0;
+    const bool p2p = St.p2p && St.comm && St.nranks > 1;
+    F.n_peer_images = p2p ? St.nranks : 0;
+    for (int r = 0; r < CLPT_MAX_PEERS; r++) F.peer_image[r] = p2p ? St.peer_image[r] : nullptr;
     if (St.flags & CLPT_FLAG_COUNTERS) {
         if (!St.counters.ptr) St.counters.resize(6);
         CU(cudaMemsetAsync(St.counters.ptr, 0, 6 * sizeof(unsigned long long), St.stream));
@@ -353,6 +482,7 @@ void clpt_state_launch_frame(int width, int height) {
     }
     St.last_engine = wavefront ? 2 : 1;
 
+    if (p2p) dist_barrier(); // every rank has finished with (reading) the previous frame
     CU(cudaEventRecord(St.ev_start, St.stream));
     if (wavefront) {
         const int n = clpt_launch_wavefront(St.scene, F, St.wf_workspace.ptr, St.wf_max_paths,
@@ -366,8 +496,11 @@ void clpt_state_launch_frame(int width, int height) {
     CU(cudaGetLastError());
     CU(cudaEventRecord(St.ev_stop, St.stream));
 
-    if (St.nranks > 1 && St.comm) {
+    if (p2p) {
+        dist_barrier(); // every rank's pixels have landed in this rank's frame
+    } else if (St.nranks > 1 && St.comm) {
         const size_t slab_px = (size_t)slab_rows_for(height) * width;
+        if (St.gathered.count != slab_px * St.nranks) St.gathered.resize(slab_px * St.nranks);
         NC(g_nccl.AllGather(St.slab.ptr, St.gathered.ptr, slab_px * 4, ncclFloat, St.comm, St.stream));
         clpt_launch_deinterleave(St.gathered.ptr, St.image.ptr, width, height, St.nranks, St.tile_rows,
                                  slab_rows_for(height), St.stream);
@@ -435,9 +568,11 @@ void CLTerminate(void) {
     if (!St.inited) return;
     release_host_kd(); // delete_kd(State.kd), src/CLState.c:223
     CU(cudaStreamSynchronize(St.stream));
+    p2p_teardown();
     if (St.comm) {
         NC(g_nccl.CommDestroy(St.comm));
         St.comm = nullptr;
+        St.comm_ranks = 0;
     }
     if (clpt_gl_registered()) clpt_gl_unregister();
     St.nodes.release();
@@ -458,6 +593,8 @@ void CLTerminate(void) {
     St.aov_uv.release();
     St.counters.release();
     St.work_counter.release();
+    St.dist_word.release();
+    St.dist_xchg.release();
     St.l2_flush.release();
     St.wf_workspace.release();
     St.wf_max_paths = 0;
@@ -686,6 +823,7 @@ void CLSetTileShard(int rank, int nranks, int tile_rows) {
     require_init("CLSetTileShard");
     if (nranks < 1 || rank < 0 || rank >= nranks || tile_rows < 4 || (tile_rows % 4) != 0)
         FATAL("CLSetTileShard: need 0 <= rank < nranks and tile_rows a positive multiple of 4");
+    p2p_teardown(); // under the sharding the mappings were made for
     St.rank = rank;
     St.nranks = nranks;
     St.tile_rows = tile_rows;
@@ -703,30 +841,42 @@ void CLDistGetUniqueId(void *id128) {
 void CLDistInit(int rank, int nranks, const void *id128, int tile_rows) {
     require_init("CLDistInit");
     nccl_load();
-    CLSetTileShard(rank, nranks, tile_rows);
+    if (nranks < 1 || rank < 0 || rank >= nranks || tile_rows < 4 || (tile_rows % 4) != 0)
+        FATAL("CLDistInit: need 0 <= rank < nranks and tile_rows a positive multiple of 4");
+    p2p_teardown(); // collective over the OLD communicator, before it goes away
     if (St.comm) {
+        CU(cudaStreamSynchronize(St.stream));
         NC(g_nccl.CommDestroy(St.comm));
         St.comm = nullptr;
+        St.comm_ranks = 0;
     }
+    St.rank = rank;
+    St.nranks = nranks;
+    St.tile_rows = tile_rows;
     if (nranks > 1) {
         ncclUniqueId id;
         memcpy(&id, id128, sizeof(id));
         CU(cudaSetDevice(St.device));
         NC(g_nccl.CommInitRank(&St.comm, nranks, id, rank));
+        St.comm_ranks = nranks;
     }
-    if (St.have_image) alloc_targets();
+    if (St.have_image) alloc_targets(); // collective: exchanges the frames' handles
 }
 
 void CLDistShutdown(void) {
+    p2p_teardown();
     if (St.comm) {
         CU(cudaStreamSynchronize(St.stream));
         NC(g_nccl.CommDestroy(St.comm));
         St.comm = nullptr;
+        St.comm_ranks = 0;
     }
     St.rank = 0;
     St.nranks = 1;
     if (St.inited && St.have_image) alloc_targets();
 }
+
+int CLDistDirectPlacement(void) { return St.p2p ? 1 : 0; }
 
 const char *CLDeviceName(void) {
     require_init("CLDeviceName");

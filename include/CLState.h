@@ -141,13 +141,22 @@ float CLEventElapsedMs(int start_slot, int stop_slot); /* synchronises stop */
 void CLFlushL2(void);                      /* overwrite a buffer larger than L2 */
 
 /* ---- multi-GPU: one process per GPU, row tiles interleaved round-robin ----
- * Rank r renders tiles t with t % nranks == r (tile = tile_rows image rows)
- * into a compact slab; CLExecute then all-gathers the slabs with NCCL and
- * de-interleaves into every rank's target.  The id is created on rank 0 with
- * CLDistGetUniqueId and carried to the others by the caller. */
+ * Rank r renders tiles t with t % nranks == r (tile = tile_rows image rows).
+ * Direct placement (default, up to 8 ranks on one node): every rank maps the
+ * other ranks' frames (CUDA IPC, peer access over NVLink) and the render kernel
+ * stores each finished pixel into all of them; CLExecute brackets the frame
+ * with two one-word barriers on the communicator and there is no gather pass.
+ * Fallback ($CLPT_P2P=0 on every rank, or the mapping fails on any rank): the
+ * rank renders into a compact slab, CLExecute all-gathers the slabs with NCCL
+ * and de-interleaves them into every rank's target.
+ * The id is created on rank 0 with CLDistGetUniqueId and carried to the others
+ * by the caller.  With a communicator, CLDistInit, CLDistShutdown,
+ * CLCreateImageHeadless, CLCreateImage, CLSetTileShard, CLExecute and
+ * CLTerminate are collective: every rank calls them in the same order. */
 void CLDistGetUniqueId(void *id128);       /* 128 bytes out; one id per CLDistInit (NCCL ids are single-use) */
 void CLDistInit(int rank, int nranks, const void *id128, int tile_rows);
 void CLDistShutdown(void);
+int CLDistDirectPlacement(void);           /* 1 while frames are peer-mapped (no gather pass), else 0 */
 /* Sharding without a communicator (each rank keeps only its own rows). */
 void CLSetTileShard(int rank, int nranks, int tile_rows);
 

@@ -1,6 +1,8 @@
-"""N > 1 on real GPUs: two ranks (one process per GPU) render their row tiles,
-CLExecute all-gathers the slabs with NCCL and de-interleaves; every rank must end
-up with the full frame, bit-identical to the single-rank frame and the oracle.
+"""N > 1 on real GPUs: two ranks (one process per GPU) render their row tiles and
+the frame is assembled on every rank -- by direct placement into peer-mapped frames
+(default) and by the NCCL all-gather + de-interleave fallback; every rank must end
+up with the full frame, bit-identical to the single-rank frame and the oracle, frame
+after frame.
 Skipped with fewer than two devices (the CPU/gloo twin is tests/test_multirank_cpu.py)."""
 import os
 import subprocess
@@ -43,19 +45,25 @@ def fresh_id():
     return idbuf.cpu().numpy().copy()
 
 ok = True
-for tile_rows, engine in ((8, 1), (4, 1), (8, 2)):
+refs = {seed: op.render(scene, cam, w, h, mode=1, depth=4, spp=5, seed=seed, flags=op.FLAG_JITTER, aov=False)["rgba"]
+        for seed in (3, 4)}
+for tile_rows, engine, direct in ((8, 1, 1), (4, 1, 1), (8, 2, 1), (8, 1, 0)):
+    os.environ["CLPT_P2P"] = str(direct)
     raw = fresh_id()
     L.CLDistInit(rank, world, raw.ctypes.data, tile_rows)
     L.CLSetEngine(engine)
-    r.set_params(mode=1, depth=4, spp=5, seed=3, flags=cl.FLAG_JITTER)
     r.create_image(w, h)
-    r.execute()
-    img = r.read_image()
-    ref = op.render(scene, cam, w, h, mode=1, depth=4, spp=5, seed=3, flags=op.FLAG_JITTER, aov=False)["rgba"]
-    same = np.array_equal(img.view(np.uint32), ref.view(np.uint32))
-    print(f"rank {rank} tile_rows {tile_rows} engine {engine}: {'ok' if same else 'MISMATCH'}", flush=True)
-    ok = ok and same
+    got_direct = L.CLDistDirectPlacement()
+    for seed in (3, 4):                # two frames back to back: no stale or torn rows
+        r.set_params(mode=1, depth=4, spp=5, seed=seed, flags=cl.FLAG_JITTER)
+        r.execute()
+        img = r.read_image()
+        same = np.array_equal(img.view(np.uint32), refs[seed].view(np.uint32)) and got_direct == direct
+        print(f"rank {rank} tile_rows {tile_rows} engine {engine} direct {got_direct} seed {seed}: "
+              f"{'ok' if same else 'MISMATCH'}", flush=True)
+        ok = ok and same
     L.CLDistShutdown()
+os.environ.pop("CLPT_P2P", None)
 r.close()
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
@@ -65,7 +73,7 @@ sys.exit(0 if int(flag.item()) == 1 else 1)
 
 
 @pytest.mark.gpu
-def test_two_rank_nccl_gather(tmp_path):
+def test_two_rank_frame_assembly(tmp_path):
     import torch
 
     if torch.cuda.device_count() < 2:
@@ -76,4 +84,4 @@ def test_two_rank_nccl_gather(tmp_path):
            "127.0.0.1", "--master-port", "29541", str(script)]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
-    assert p.stdout.count(": ok") == 6, p.stdout
+    assert p.stdout.count(": ok") == 16, p.stdout
