@@ -287,6 +287,7 @@ def run_animated(a):
     from clpathtracer_b200 import scenes
 
     L = cl.lib()
+    a.sah_bins = 32  # a per-frame rebuild wants the fast builder: binned planes, no clipping
     tv, tc, _ = scenes.heightfield(a.grid, False)
     sv, sf = icosphere(3)
     sv = sv * np.float32(0.12)
@@ -311,7 +312,7 @@ def run_animated(a):
         if pos.s[1] < 0.3 and vel.s[1] < 0:
             vel.s[1] = -vel.s[1]
         verts = np.concatenate([tv, sv + np.array(pos.s[:3], dtype=np.float32)])
-        scene = cl.build_kd_sah(verts, corners, None, intersect_cost=1.0, empty_bonus=0.9)
+        scene = cl.build_kd_sah(verts, corners, None, nbins=a.sah_bins, intersect_cost=1.0, empty_bonus=0.9, clip=False)
         t1 = time.perf_counter()
         r.set_meshes(scene)
         t2 = time.perf_counter()

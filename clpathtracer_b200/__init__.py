@@ -100,7 +100,7 @@ def lib() -> C.CDLL:
         "LoadModel": (i, [C.c_char_p, C.POINTER(KD)]),
         "load_obj_lists": (i, [C.c_char_p, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
         "write_obj": (i, [C.c_char_p, vp, vp, vp]),
-        "kd_set_build_params": (None, [i, i]),
+        "kd_set_build_params": (None, [i, i]), "kd_set_sah_clip": (None, [i]),
         "AddPhysObject": (None, [vp, vp]), "PhysStep": (None, [C.c_double]), "PhysTerminate": (None, []),
         # boundary
         "CLInit": (None, [C.c_char_p, C.c_char_p]), "CLTerminate": (None, []),
@@ -221,9 +221,12 @@ def build_kd(verts: np.ndarray, corners: np.ndarray, norms: np.ndarray | None = 
 
 def build_kd_sah(verts: np.ndarray, corners: np.ndarray, norms: np.ndarray | None = None,
                  max_depth: int | None = None, nbins: int = 32, traversal_cost: float = 1.0,
-                 intersect_cost: float = 1.0, empty_bonus: float = 0.9, path: str | None = None) -> Scene:
-    """SAH kd-tree (extension, clpt_host.h build_kd_sah): same wire format and ropes."""
+                 intersect_cost: float = 1.0, empty_bonus: float = 0.9, path: str | None = None,
+                 clip: bool = True) -> Scene:
+    """SAH kd-tree (extension, clpt_host.h build_kd_sah): same wire format and ropes.
+    nbins <= 0: candidate planes on every triangle bound (exact sweep); clip: perfect splits."""
     L = lib()
+    L.kd_set_sah_clip(1 if clip else 0)
     v4 = _as_vec4(verts)
     n4 = _as_vec4(norms) if norms is not None and len(norms) else None
     if max_depth is None:

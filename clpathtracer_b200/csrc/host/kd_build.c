@@ -367,9 +367,17 @@ clip_bounds(const sah_params *P, int id, const float *cmin, const float *cmax, f
             src[k][c] = v.s[c];
         }
     }
+    double tmin[3], tmax[3]; /* the whole triangle's extent: faces it does not reach clip nothing */
+    for (int c = 0; c < 3; c++) {
+        tmin[c] = fmin(fmin(src[0][c], src[1][c]), src[2][c]);
+        tmax[c] = fmax(fmax(src[0][c], src[1][c]), src[2][c]);
+    }
     for (int axis = 0; axis < 3 && np > 0; axis++) {
         for (int side = 0; side < 2 && np > 0; side++) {
             const double plane = side ? cmax[axis] : cmin[axis];
+            if (side ? tmax[axis] <= plane : tmin[axis] >= plane) {
+                continue;
+            }
             int nq = 0;
             for (int k = 0; k < np; k++) {
                 const double *p = src[k], *q = src[(k + 1) % np];
@@ -934,14 +942,21 @@ build_kd_ex(cl_int3 *tris, Vector3 *verts, Vector3 *norms, const char *path,
     return build_tree(tris, verts, norms, path, depth, nbins, NULL);
 }
 
+static int g_sah_clip = 1;
+
+void
+kd_set_sah_clip(int enable) {
+    g_sah_clip = enable != 0;
+}
+
 kd
 build_kd_sah(cl_int3 *tris, Vector3 *verts, Vector3 *norms, const char *path,
              int max_depth, int nbins, float traversal_cost, float intersect_cost,
              float empty_bonus) {
     /* nbins <= 0: every triangle bound is a candidate at every cell size (sorted sweep) */
     sah_params P = { max_depth, nbins, traversal_cost, intersect_cost, empty_bonus,
-                     nbins > 0 ? SAH_EXACT_BELOW : 0x7fffffff, 1, tris, verts };
-    const char *e = getenv("CLPT_SAH_CLIP");
+                     nbins > 0 ? SAH_EXACT_BELOW : 0x7fffffff, g_sah_clip, tris, verts };
+    const char *e = getenv("CLPT_SAH_CLIP"); /* overrides kd_set_sah_clip, for experiments */
     if (e) P.clip = atoi(e);
     return build_tree(tris, verts, norms, path, 0, 0, &P);
 }

@@ -133,6 +133,10 @@ int LoadModel(const char *filename, kd *model);
 int load_obj_lists(const char *filename, Vector3 **verts, Vector3 **norms, cl_int3 **tris);
 int write_obj(const char *filename, const Vector3 *verts, const Vector3 *norms, const cl_int3 *tris);
 void kd_set_build_params(int depth, int nbins); /* depth/nbins used by LoadModel's build */
+/* build_kd_sah: re-derive a straddling triangle's bounds from the triangle clipped to
+ * each child cell ("perfect splits").  Default on: 15-20% fewer triangle tests on
+ * scenes with large or thin triangles, ~10% more build time.  Off for per-frame rebuilds. */
+void kd_set_sah_clip(int enable);
 
 /* ------------------------------------------------------------------ physics
  * Explicit Euler pos += vel*dt over registered pointer pairs.
