@@ -438,6 +438,12 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, kernel_total_ms, e2e_ms = t.tolist()
+    per_rank_kernel_ms = None
+    if world > 1:  # how evenly the row tiles split the work: each rank's mean render-kernel time
+        mine = torch.tensor([float(np.mean(kern_ms))], dtype=torch.float64, device="cuda")
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        per_rank_kernel_ms = [round(float(x.item()), 4) for x in every]
 
     if rank == 0:
         ms_per_step = total_ms / a.steps
@@ -464,6 +470,7 @@ def main():
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": 64,
                     "d2h_bytes_per_step": a.width * a.height * 16, "ms_per_step": round(e2e_ms / a.steps, 4)},
             "gpu_launches": launches,
+            "per_rank_kernel_ms": per_rank_kernel_ms,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,

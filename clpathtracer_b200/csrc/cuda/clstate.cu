@@ -167,6 +167,7 @@ struct {
     int comm_ranks = 0;
     // direct placement (peer-mapped frames), see p2p_setup
     bool p2p = false;
+    int p2p_self = -1; // this rank's slot in peer_image (its own frame, not a mapping)
     float4 *peer_image[CLPT_MAX_PEERS] = {};
     DevBuf<int> dist_word;           // operand of the barrier all-reduce
     DevBuf<unsigned char> dist_xchg; // handle exchange staging
@@ -306,7 +307,7 @@ int dist_min(int v) {
 
 void p2p_close_mappings() {
     for (int r = 0; r < CLPT_MAX_PEERS; r++) {
-        if (St.peer_image[r] && St.peer_image[r] != St.image.ptr) {
+        if (St.peer_image[r] && r != St.p2p_self) {
             const cudaError_t e = cudaIpcCloseMemHandle(St.peer_image[r]);
             if (e != cudaSuccess) {
                 fprintf(stderr, "rank %d: unmapping rank %d's frame: %s\n", St.rank, r, cudaGetErrorName(e));
@@ -315,6 +316,7 @@ void p2p_close_mappings() {
         }
         St.peer_image[r] = nullptr;
     }
+    St.p2p_self = -1;
 }
 
 // Collective over the communicator.  Must run before a mapped frame is freed or resized
@@ -358,6 +360,7 @@ void p2p_setup() {
     CU(cudaStreamSynchronize(St.stream));
     int ok = 1;
     for (size_t r = 0; r < n; r++) ok &= all[r].ok;
+    St.p2p_self = St.rank;
     for (size_t r = 0; ok && r < n; r++) {
         if ((int)r == St.rank) {
             St.peer_image[r] = St.image.ptr;
@@ -702,6 +705,7 @@ void CLSetMaxLeafVisits(int cap) {
 void CLDeleteImage(void) {
     require_init("CLDeleteImage");
     if (!St.have_image) FATAL("CLDeleteImage: no render target"); // clReleaseMemObject(0) errors too
+    p2p_teardown(); // collective: no rank frees a frame its peers still map
     if (clpt_gl_registered()) clpt_gl_unregister();
     St.image.release();
     St.slab.release();

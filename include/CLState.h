@@ -151,8 +151,8 @@ void CLFlushL2(void);                      /* overwrite a buffer larger than L2 
  * and de-interleaves them into every rank's target.
  * The id is created on rank 0 with CLDistGetUniqueId and carried to the others
  * by the caller.  With a communicator, CLDistInit, CLDistShutdown,
- * CLCreateImageHeadless, CLCreateImage, CLSetTileShard, CLExecute and
- * CLTerminate are collective: every rank calls them in the same order. */
+ * CLCreateImageHeadless, CLCreateImage, CLDeleteImage, CLSetTileShard, CLExecute
+ * and CLTerminate are collective: every rank calls them in the same order. */
 void CLDistGetUniqueId(void *id128);       /* 128 bytes out; one id per CLDistInit (NCCL ids are single-use) */
 void CLDistInit(int rank, int nranks, const void *id128, int tile_rows);
 void CLDistShutdown(void);

@@ -85,3 +85,4 @@ def test_two_rank_frame_assembly(tmp_path):
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert p.stdout.count(": ok") == 16, p.stdout
+    print(p.stderr[-1500:])  # shown with -s: mapping diagnostics
