@@ -79,13 +79,19 @@ struct ClptFrame {
     float2 *aov_uv;
     unsigned long long *counters; // 6 counters, may be null
     unsigned int *work_counter;   // warp-tile claim counter of the persistent render kernel
+    // Claim direction: warp tiles are handed out in screen order, top to bottom, or with
+    // CLPT_F_REVERSE bottom to top.  Every warp tile adds its duration to
+    // row_cost[its block row] (null = not recorded); CLExecute looks at where one frame's
+    // cost sits and points the next frame's claims so that they END at the cheap side.
+    unsigned long long *row_cost;
     int blocks_x, n_warp_tiles;   // filled in by clpt_launch_render
 };
 
-enum { CLPT_F_JITTER = 1, CLPT_F_ACCUMULATE = 2, CLPT_F_COUNTERS = 4 };
+enum { CLPT_F_JITTER = 1, CLPT_F_ACCUMULATE = 2, CLPT_F_COUNTERS = 4, CLPT_F_REVERSE = 0x100 /* internal */ };
 
 // render_kernel.cu
 void clpt_launch_render(const ClptScene &scene, const ClptFrame &frame, int sm_count, cudaStream_t stream);
+int clpt_render_block_rows(const ClptFrame &frame); // rows of blocks the launch will walk (size of row_cost)
 void clpt_launch_deinterleave(const float4 *gathered, float4 *image, int width, int height,
                               int nranks, int tile_rows, int slab_rows, cudaStream_t stream);
 void clpt_launch_fill(float4 *dst, size_t n, float value, cudaStream_t stream);

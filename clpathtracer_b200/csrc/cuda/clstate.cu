@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -153,6 +154,14 @@ struct {
     DevBuf<float2> aov_uv;
     DevBuf<unsigned long long> counters;
     DevBuf<unsigned int> work_counter;
+    // claim direction (ClptFrame::row_cost): where this frame's cost sits points the next frame
+    DevBuf<unsigned long long> row_cost;
+    unsigned long long *host_row_cost = nullptr; // pinned
+    int row_capacity = 0;
+    int row_count = 0;         // rows the current direction was measured on
+    long long row_key[8] = {}; // ... and under which image / sharding / parameters
+    bool claim_reverse = false;
+    unsigned long long frames_rendered = 0;
     unsigned long long host_counters[6] = { 0 };
     float last_kernel_ms = 0;
     int last_launches = 0;
@@ -456,6 +465,7 @@ void clpt_state_launch_frame(int width, int height) {
     if (!St.work_counter.ptr) St.work_counter.resize(1);
     F.work_counter = St.work_counter.ptr;
     F.blocks_x = F.n_warp_tiles = 0;
+    F.row_cost = nullptr;
     const bool p2p = St.p2p && St.comm && St.nranks > 1;
     F.n_peer_images = p2p ? St.nranks : 0;
     for (int r = 0; r < CLPT_MAX_PEERS; r++) F.peer_image[r] = p2p ? St.peer_image[r] : nullptr;
@@ -485,6 +495,33 @@ void clpt_state_launch_frame(int width, int height) {
     }
     St.last_engine = wavefront ? 2 : 1;
 
+    // Claim direction (megakernel): decided from the previous frame's per-row cost under
+    // the same image, sharding and parameters.  $CLPT_ROW_ORDER=0 turns it off.
+    int order_rows = 0;
+    if (!wavefront) {
+        const char *e = getenv("CLPT_ROW_ORDER");
+        if (!(e && atoi(e) == 0)) order_rows = clpt_render_block_rows(F);
+        // the bookkeeping (a memset and a small copy, ~15 us) is only worth it on frames long
+        // enough to have a tail: skipped while the previous frame took under half a millisecond
+        if (St.frames_rendered > 0 && St.last_kernel_ms < 0.5f) order_rows = 0;
+    }
+    if (order_rows > 0) {
+        const long long key[8] = { width, height, St.spp, St.mode, St.depth, St.rank, St.nranks, St.tile_rows };
+        if (order_rows != St.row_count || memcmp(key, St.row_key, sizeof(key)) != 0) {
+            St.claim_reverse = false;
+            St.row_count = order_rows;
+            memcpy(St.row_key, key, sizeof(key));
+        }
+        if (order_rows > St.row_capacity) {
+            if (St.host_row_cost) CU(cudaFreeHost(St.host_row_cost));
+            CU(cudaMallocHost((void **)&St.host_row_cost, (size_t)order_rows * sizeof(unsigned long long)));
+            St.row_cost.resize((size_t)order_rows);
+            St.row_capacity = order_rows;
+        }
+        CU(cudaMemsetAsync(St.row_cost.ptr, 0, (size_t)order_rows * sizeof(unsigned long long), St.stream));
+        F.row_cost = St.row_cost.ptr;
+        if (St.claim_reverse) F.flags |= CLPT_F_REVERSE;
+    }
     if (p2p) dist_barrier(); // every rank has finished with (reading) the previous frame
     CU(cudaEventRecord(St.ev_start, St.stream));
     if (wavefront) {
@@ -498,6 +535,10 @@ void clpt_state_launch_frame(int width, int height) {
     }
     CU(cudaGetLastError());
     CU(cudaEventRecord(St.ev_stop, St.stream));
+    if (order_rows > 0) {
+        CU(cudaMemcpyAsync(St.host_row_cost, St.row_cost.ptr, (size_t)order_rows * sizeof(unsigned long long),
+                           cudaMemcpyDeviceToHost, St.stream));
+    }
 
     if (p2p) {
         dist_barrier(); // every rank's pixels have landed in this rank's frame
@@ -529,6 +570,31 @@ void clpt_state_launch_frame(int width, int height) {
     }
     CU(cudaStreamSynchronize(St.stream)); // clFinish, src/CLState.c:212
     CU(cudaEventElapsedTime(&St.last_kernel_ms, St.ev_start, St.ev_stop));
+    St.frames_rendered++;
+    if (order_rows >= 16) {
+        // Claim the expensive rows EARLY: what matters at the end of a frame is the longest
+        // tile still running, and cheap rows after the expensive ones give no cover (sky
+        // tiles take microseconds; the grazing rows under the horizon up to a millisecond).
+        // Find the costliest band (5-row moving sum) and start from the end it is nearer to;
+        // it has to sit clearly in the far half (beyond 55%) to flip, so noise does not.
+        unsigned long long best = 0, sum = 0;
+        int best_at = 0;
+        for (int i = 0; i < order_rows; i++) {
+            sum += St.host_row_cost[i];
+            if (i >= 5) sum -= St.host_row_cost[i - 5];
+            if (sum > best) {
+                best = sum;
+                best_at = i - 2;
+            }
+        }
+        const double where = (double)best_at / (double)(order_rows - 1); // 0 = first row claimed forward
+        if (!St.claim_reverse && where > 0.55) St.claim_reverse = true;
+        else if (St.claim_reverse && where < 0.45) St.claim_reverse = false;
+        if (getenv("CLPT_VERBOSE") && atoi(getenv("CLPT_VERBOSE")) >= 3) {
+            fprintf(stderr, "CLExecute: costliest rows at %.2f of %d, next frame claims %s\n", where, order_rows,
+                    St.claim_reverse ? "bottom-up" : "top-down");
+        }
+    }
     if (St.flags & CLPT_FLAG_COUNTERS) {
         CU(cudaMemcpy(St.host_counters, St.counters.ptr, sizeof(St.host_counters), cudaMemcpyDeviceToHost));
     }
@@ -596,6 +662,11 @@ void CLTerminate(void) {
     St.aov_uv.release();
     St.counters.release();
     St.work_counter.release();
+    St.row_cost.release();
+    if (St.host_row_cost) CU(cudaFreeHost(St.host_row_cost));
+    St.host_row_cost = nullptr;
+    St.row_capacity = St.row_count = 0;
+    St.claim_reverse = false;
     St.dist_word.release();
     St.dist_xchg.release();
     St.l2_flush.release();

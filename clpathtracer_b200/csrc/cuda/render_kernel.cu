@@ -128,14 +128,28 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
     // (40% idle on a 4 ms frame).  Tile t = ((by * tiles_x + bx) * 8 + w): the same
     // 4 x 2 arrangement of warp tiles as a block of the static mapping, so
     // consecutive claims are neighbours on screen.
+    // Claim direction.  A warp tile is a whole pixel's samples and bounces (up to ~1 ms of
+    // one warp), so a frame whose most expensive tiles are claimed LATE ends with a few
+    // warps busy for ~0.9 ms while the rest of the GPU idles: 2% of a 37 ms frame, 13% of
+    // one GPU's share of it on 8 GPUs.  CLExecute therefore measures where the cost of a
+    // frame sits (row_cost) and has the next one start from the end nearer to its costliest
+    // rows.  Screen order is kept either way: neighbouring claims stay neighbours in the
+    // tree (sorting rows by cost outright was measured and loses more in locality than it
+    // wins, profiles/r01_experiments.json).
+    __shared__ unsigned tile_t0[8], tile_row[8]; // kept out of registers across the trace
     const unsigned bx_count = (unsigned)F.blocks_x, n_tiles = (unsigned)F.n_warp_tiles;
     for (;;) {
         unsigned t = 0;
-        if (lane == 0) t = atomicAdd(F.work_counter, 1u);
+        if (lane == 0) {
+            t = atomicAdd(F.work_counter, 1u);
+            tile_t0[warp] = (unsigned)clock();
+        }
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= n_tiles) break;
+        if (F.flags & CLPT_F_REVERSE) t = n_tiles - 1u - t;
         const unsigned w = t & 7u, b = t >> 3;
         const int bx = (int)(b % bx_count), by = (int)(b / bx_count);
+        if (lane == 0) tile_row[warp] = (unsigned)by;
         const int x = (bx * 4 + (int)(w & 3u)) * tw + (pslot & (tw - 1));
         const int ly = (by * 2 + (int)(w >> 2)) * th + pslot / tw; // row within this rank's slab
         const int y = slab_row_to_image_row(F, ly);
@@ -174,6 +188,9 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
             acc = mk(r, g, bl);
         }
         if (valid && sslot == 0) store_pixel(F, x, ly, acc, spp);
+        if (lane == 0 && F.row_cost) {
+            atomicAdd(F.row_cost + tile_row[warp], (unsigned long long)((unsigned)clock() - tile_t0[warp]));
+        }
     }
     if (COUNT) {
         unsigned v[6] = { cn.rays, cn.splits, cn.leaves, cn.tris, cn.shade_vn, cn.capped };
@@ -226,6 +243,13 @@ void launch_mode(const ClptScene &scene, const ClptFrame &frame, unsigned grid, 
 }
 
 } // namespace
+
+int clpt_render_block_rows(const ClptFrame &frame) {
+    int tw, th;
+    warp_tile_dims(5 - frame.log2_sample_lanes, tw, th);
+    const int block_h = 2 * th;
+    return (frame.local_rows + block_h - 1) / block_h;
+}
 
 void clpt_launch_render(const ClptScene &scene, const ClptFrame &frame_in, int sm_count, cudaStream_t stream) {
     ClptFrame frame = frame_in;
