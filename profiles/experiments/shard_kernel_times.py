@@ -1,3 +1,8 @@
+"""Render-kernel time of one rank's share of the bench frame on ONE GPU (CLSetTileShard without a
+communicator), with the claim-direction heuristic off/on ($CLPT_ROW_ORDER).  Source of
+profiles/r01_experiments.json: frame_tail_and_claim_direction.  Run on a GPU box:
+    python profiles/experiments/shard_kernel_times.py
+"""
 import os, sys, json, numpy as np
 sys.path.insert(0, os.environ.get("GRAFT_REPO_ROOT", "/root/repo"))
 import torch
