@@ -60,7 +60,8 @@ def scene_cache(clpt):
             raise KeyError(name)
         if sah:
             # sah="exact": candidate planes on every triangle bound at every cell size
-            s = clpt.build_kd_sah(v, c, nn, nbins=0 if sah == "exact" else 32, intersect_cost=1.0, empty_bonus=0.9)
+            s = clpt.build_kd_sah(v, c, nn, nbins=0 if sah == "exact" else 32, intersect_cost=1.0, empty_bonus=0.9,
+                                  clip=sah != "noclip")
         else:
             s = clpt.build_kd(v, c, nn, depth=depth, nbins=nbins)
         cache[key] = (s, extras)

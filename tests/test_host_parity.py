@@ -247,12 +247,15 @@ def test_build_kd_ex_invariants(clpt, depth, nbins):
     assert st["leaves"] * 2 - 1 == st["nodes"]
 
 
+@pytest.mark.parametrize("variant", [dict(), dict(nbins=0), dict(clip=False), dict(nbins=0, clip=False)],
+                         ids=["binned", "exact", "binned-noclip", "exact-noclip"])
 @pytest.mark.parametrize("name", ["hf40", "cornell", "soup3000", "hf4n"])
-def test_build_kd_sah_invariants(clpt, name):
+def test_build_kd_sah_invariants(clpt, name, variant):
     """The SAH builder (extension) emits the same wire format: preorder nodes,
-    contiguous leaf runs, every triangle referenced, valid ropes."""
+    contiguous leaf runs, every triangle referenced, valid ropes -- with binned or
+    exact-sweep candidate planes, with and without perfect splits."""
     v, c, n = _scene_inputs(name)
-    s = clpt.build_kd_sah(v, c, n, intersect_cost=1.0, empty_bonus=0.9)
+    s = clpt.build_kd_sah(v, c, n, intersect_cost=1.0, empty_bonus=0.9, **variant)
     _check_tree_invariants(s)
     st = s.stats()
     assert st["leaves"] * 2 - 1 == st["nodes"]
@@ -267,8 +270,9 @@ def test_build_kd_thread_independent(clpt):
     """The parallel evaluation order must not change a single byte."""
     code = ("import sys,hashlib;sys.path.insert(0,%r);import clpathtracer_b200 as cl;"
             "from clpathtracer_b200 import scenes;s=cl.build_kd(*scenes.heightfield(150,False),depth=18);"
-            "t=cl.build_kd_sah(*scenes.heightfield(150,False));"
-            "print(hashlib.sha256(s.nodes.tobytes()+s.tri_indices.tobytes()+t.nodes.tobytes()+t.tri_indices.tobytes()).hexdigest())") % str(
+            "t=cl.build_kd_sah(*scenes.heightfield(150,False));u=cl.build_kd_sah(*scenes.soup(20000),nbins=0);"
+            "print(hashlib.sha256(s.nodes.tobytes()+s.tri_indices.tobytes()+t.nodes.tobytes()+t.tri_indices.tobytes()"
+            "+u.nodes.tobytes()+u.tri_indices.tobytes()).hexdigest())") % str(
                 Path(__file__).resolve().parents[1])
     digests = set()
     for threads in ("1", "3", "8"):

@@ -79,7 +79,7 @@ def _brute_force(scene, cam, w, h):
                                              # exact-sweep SAH puts planes ON mesh grid lines; hf21 keeps the
                                              # centred camera's x = 0 pixel column off them (kd_build.c, partition)
                                              ("hf21", "canonical", "exact"), ("cornell", "cornell", "exact"),
-                                             ("soup500", "cornell", "exact")])
+                                             ("soup500", "cornell", "exact"), ("soup500", "cornell", "noclip")])
 def test_traversal_against_brute_force(clpt, oracle, scene_cache, name, camera, sah):
     """Rope traversal must find the globally closest front-facing hit.  The
     reference traversal is not watertight (split-plane
