@@ -23,8 +23,9 @@
  * 32 B per reference instead of an 80 B struct copy), the candidate planes of
  * large nodes are evaluated concurrently (each candidate still sums its
  * triangles in list order, so every fp32 cost is bit-identical to a serial
- * evaluation), subtrees are built as OpenMP tasks into a linked tree, and the
- * preorder arrays are emitted in one pass at the end.  Depth and bin count
+ * evaluation), subtrees are built as OpenMP tasks into a linked tree whose
+ * nodes know their subtree sizes, so the preorder arrays are then written -- and
+ * the ropes linked -- by parallel tasks at known offsets.  Depth and bin count
  * are run-time parameters.
  */
 #include <float.h>
