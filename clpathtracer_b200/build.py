@@ -20,7 +20,7 @@ CSRC = PKG / "csrc"
 OBJ = PKG / "_build"
 LIB = PKG / "libclpt.so"
 
-HOST_C = ["host/hostlist.c", "host/vecmath.c", "host/kd_build.c", "host/model_io.c"]
+HOST_C = ["host/hostlist.c", "host/vecmath.c", "host/kd_build.c", "host/model_io.c", "host/frame_sched.c"]
 HOST_CXX = ["cuda/scene_pack.cpp"]
 CUDA = ["cuda/render_kernel.cu", "cuda/wavefront.cu", "cuda/gl_interop.cu", "cuda/clstate.cu",
         "cuda/clhandler.cu"]
@@ -61,6 +61,7 @@ def build(force: bool = False, verbose: bool = False, defines: list[str] | None 
     OBJ.mkdir(exist_ok=True)
     inc = ["-I" + str(ROOT / "include"), "-I" + str(CSRC / "cuda")]
     headers = list((ROOT / "include").glob("*.h")) + list((CSRC / "cuda").glob("*.h")) + \
+        list((CSRC / "host").glob("*.h")) + \
         list((CSRC / "cuda").glob("*.cuh")) + [Path(__file__)]
     objs: list[Path] = []
     for rel in HOST_C:

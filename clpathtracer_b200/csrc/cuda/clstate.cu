@@ -20,6 +20,7 @@
 #include "CLState.h"
 #include "clpt_device.cuh"
 #include "clpt_host.h"
+#include "../host/frame_sched.h"
 #include "scene_pack.h"
 
 #define CU(call) handle_err((int)(call), __FILE__, __LINE__)
@@ -571,25 +572,9 @@ void clpt_state_launch_frame(int width, int height) {
     CU(cudaStreamSynchronize(St.stream)); // clFinish, src/CLState.c:212
     CU(cudaEventElapsedTime(&St.last_kernel_ms, St.ev_start, St.ev_stop));
     St.frames_rendered++;
-    if (order_rows >= 16) {
-        // Claim the expensive rows EARLY: what matters at the end of a frame is the longest
-        // tile still running, and cheap rows after the expensive ones give no cover (sky
-        // tiles take microseconds; the grazing rows under the horizon up to a millisecond).
-        // Find the costliest band (5-row moving sum) and start from the end it is nearer to;
-        // it has to sit clearly in the far half (beyond 55%) to flip, so noise does not.
-        unsigned long long best = 0, sum = 0;
-        int best_at = 0;
-        for (int i = 0; i < order_rows; i++) {
-            sum += St.host_row_cost[i];
-            if (i >= 5) sum -= St.host_row_cost[i - 5];
-            if (sum > best) {
-                best = sum;
-                best_at = i - 2;
-            }
-        }
-        const double where = (double)best_at / (double)(order_rows - 1); // 0 = first row claimed forward
-        if (!St.claim_reverse && where > 0.55) St.claim_reverse = true;
-        else if (St.claim_reverse && where < 0.45) St.claim_reverse = false;
+    if (order_rows > 0) { // next frame starts from the end nearer to this frame's costliest rows
+        double where = 0.0;
+        St.claim_reverse = clpt_claim_direction(St.host_row_cost, order_rows, St.claim_reverse ? 1 : 0, &where) != 0;
         if (getenv("CLPT_VERBOSE") && atoi(getenv("CLPT_VERBOSE")) >= 3) {
             fprintf(stderr, "CLExecute: costliest rows at %.2f of %d, next frame claims %s\n", where, order_rows,
                     St.claim_reverse ? "bottom-up" : "top-down");
