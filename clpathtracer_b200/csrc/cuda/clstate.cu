@@ -743,7 +743,7 @@ void CLSetRenderParams(int mode, int depth, int spp, unsigned int seed, int flag
     St.depth = depth;
     St.spp = spp;
     St.seed = seed;
-    St.flags = flags;
+    St.flags = flags & (CLPT_FLAG_JITTER | CLPT_FLAG_ACCUMULATE | CLPT_FLAG_COUNTERS); // other bits are internal
 }
 
 void CLSetEngine(int engine) {
