@@ -2,8 +2,10 @@
 
 Tiles of `tile_rows` image rows are dealt round-robin: tile t belongs to rank
 t % nranks and is that rank's local tile t // nranks.  Each rank renders its
-tiles into a compact slab of ceil(tiles / nranks) * tile_rows rows; the slabs
-are all-gathered and de-interleaved.  This module is the host-side statement of
+tiles into a compact slab of ceil(tiles / nranks) * tile_rows rows and, with
+direct placement, straight into row slab_row -> image row of every rank's frame;
+on the fallback path the slabs are all-gathered and de-interleaved.  This module
+is the host-side statement of
 that mapping; csrc/cuda/clstate.cu (slab_rows_for / local_rows_for) and the
 kernels in render_kernel.cu implement the same arithmetic on the device.
 """
