@@ -52,8 +52,10 @@ def parse_args():
     ap.add_argument("--sah-ci", type=float, default=1.0)
     ap.add_argument("--sah-bonus", type=float, default=0.9)
     ap.add_argument("--sah-bins", type=int, default=0, help="0: exact sweep over all triangle bounds")
-    ap.add_argument("--mode", default="mirror", choices=["mirror", "path"],
-                    help="mirror: the reference's bounce (mode B); path: diffuse BSDF extension (mode C)")
+    ap.add_argument("--mode", default="mirror", choices=["normal", "mirror", "path"],
+                    help="normal: as shipped, first-hit normal colour (mode A); mirror: the reference's bounce "
+                         "(mode B); path: diffuse BSDF extension (mode C)")
+    ap.add_argument("--no-jitter", action="store_true", help="pixel-corner rays exactly as the reference generates them")
     ap.add_argument("--engine", type=int, default=int(os.environ.get("CLPT_ENGINE", "0")),
                     help="0 auto, 1 megakernel, 2 wavefront")
     ap.add_argument("--tile-rows", type=int, default=8)
@@ -378,7 +380,7 @@ def main():
         L.CLDistInit(rank, world, raw.ctypes.data, a.tile_rows)
     r.create_image(a.width, a.height)
     a.direct_placement = int(L.CLDistDirectPlacement()) if world > 1 else 1
-    flags = cl.FLAG_JITTER | (cl.FLAG_ACCUMULATE if a.progressive else 0)
+    flags = (0 if a.no_jitter else cl.FLAG_JITTER) | (cl.FLAG_ACCUMULATE if a.progressive else 0)
 
     def barrier():
         if world > 1:
@@ -386,7 +388,7 @@ def main():
         torch.cuda.synchronize()
 
     # instrumented frame: counts rays / node / triangle work for this rank's rows
-    mode = cl.MODE_PATH if a.mode == "path" else cl.MODE_MIRROR
+    mode = {"normal": cl.MODE_NORMAL, "mirror": cl.MODE_MIRROR, "path": cl.MODE_PATH}[a.mode]
     r.set_params(mode=mode, depth=a.depth, spp=a.spp, seed=a.seed, flags=flags | cl.FLAG_COUNTERS)
     r.execute()
     counters = r.counters()

@@ -57,6 +57,10 @@ struct ClptScene {
 };
 
 #define CLPT_MAX_PEERS 8
+// Leaves with at least this many triangles are shared between the lanes of a warp by the
+// cooperative engine (clpt_trace.cuh: closest_hit_coop); also the "fat leaf" of the
+// automatic engine choice.
+#define CLPT_COOP_LEAF_MIN 8
 
 struct ClptFrame {
     float cam[16]; // row-major inverse camera matrix
@@ -87,7 +91,8 @@ struct ClptFrame {
     int blocks_x, n_warp_tiles;   // filled in by clpt_launch_render
 };
 
-enum { CLPT_F_JITTER = 1, CLPT_F_ACCUMULATE = 2, CLPT_F_COUNTERS = 4, CLPT_F_REVERSE = 0x100 /* internal */ };
+enum { CLPT_F_JITTER = 1, CLPT_F_ACCUMULATE = 2, CLPT_F_COUNTERS = 4, CLPT_F_REVERSE = 0x100 /* internal */,
+       CLPT_F_COOP = 0x200 /* internal: warp-cooperative leaves (engine 2) */ };
 
 // render_kernel.cu
 void clpt_launch_render(const ClptScene &scene, const ClptFrame &frame, int sm_count, cudaStream_t stream);
@@ -97,11 +102,3 @@ void clpt_launch_deinterleave(const float4 *gathered, float4 *image, int width, 
 void clpt_launch_fill(float4 *dst, size_t n, float value, cudaStream_t stream);
 void clpt_launch_normalise(const float4 *src, float4 *dst, size_t n, cudaStream_t stream);
 const void *clpt_render_kernel_symbol(void);
-
-// wavefront.cu: the same frame as clpt_launch_render for modes 0/1, organised as
-// generate / trace / shade / resolve passes over ray queues in `workspace`
-// (clpt_wavefront_workspace_bytes(max_paths) bytes).  Returns the number of
-// kernels launched, or -1 if the workspace cannot hold one image row.
-size_t clpt_wavefront_workspace_bytes(size_t max_paths);
-int clpt_launch_wavefront(const ClptScene &scene, const ClptFrame &frame, void *workspace, size_t max_paths,
-                          int sm_count, cudaStream_t stream);

@@ -167,10 +167,9 @@ struct {
     float last_kernel_ms = 0;
     int last_launches = 0;
     DevBuf<unsigned char> l2_flush;
-    int engine = 0; // 0 auto, 1 megakernel, 2 wavefront
+    int engine = 0;      // 0 auto, 1 lane-per-ray leaves, 2 warp-cooperative leaves
+    int auto_engine = 1; // what "auto" means for the current tree (decided in upload_scene)
     int last_engine = 1;
-    DevBuf<unsigned char> wf_workspace;
-    size_t wf_max_paths = 0;
 
     int rank = 0, nranks = 1, tile_rows = 8;
     ncclComm_t comm = nullptr;
@@ -260,6 +259,20 @@ void upload_scene(const kdnode *nodes, size_t node_bytes, const int *tri_indices
     }
     rebuild_scene_struct();
     St.have_scene = true;
+    // "automatic" engine for this tree: warp-cooperative leaves when most triangle slots
+    // live in fat leaves (the reference builder's DEPTH-15 trees at >= ~50k triangles)
+    {
+        size_t fat_refs = 0;
+        for (int l = 0; l < packed.n_leaves; l++) {
+            int count;
+            memcpy(&count, &packed.leaves[4 * (size_t)l + 1].w, sizeof(int));
+            if (count >= CLPT_COOP_LEAF_MIN) fat_refs += (size_t)count;
+        }
+        St.auto_engine = (packed.n_refs > 0 && fat_refs * 2 > (size_t)packed.n_refs) ? 2 : 1;
+        if (const char *e = getenv("CLPT_ENGINE")) {
+            if (atoi(e) == 1 || atoi(e) == 2) St.auto_engine = atoi(e);
+        }
+    }
     if (timing) {
         const auto t2 = std::chrono::steady_clock::now();
         fprintf(stderr, "CLSetMeshes: pack %.3f ms, upload %.3f ms (%d nodes, %d leaves, %d triangle slots, %zu table cells)\n",
@@ -476,30 +489,15 @@ void clpt_state_launch_frame(int width, int height) {
         F.counters = St.counters.ptr;
     }
 
-    // Engine.  Measured on the bench workload (profiles/r01_experiments.json)
-    // the megakernel with its sample-lane mapping is faster (57.7 ms against 91.3 ms
-    // for the best wavefront setting), so "automatic" means megakernel; the wavefront
-    // engine stays selectable and is held to the same bit-exact parity tests.
-    bool wavefront = St.engine == 2;
-    if (St.mode == CLPT_MODE_PATH) wavefront = false; // mode C exists in the megakernel only
-    if (wavefront) {
-        const size_t want_paths = (size_t)F.local_rows * width * (size_t)(St.spp < 1 ? 1 : St.spp);
-        size_t cap = 48u << 20; // paths per chunk
-        if (const char *env = getenv("CLPT_WF_MAX_PATHS")) cap = (size_t)atoll(env);
-        const size_t row_paths = (size_t)width * (size_t)(St.spp < 1 ? 1 : St.spp);
-        size_t paths = want_paths < cap ? want_paths : cap;
-        if (paths < row_paths) paths = row_paths;
-        if (St.wf_max_paths != paths) {
-            St.wf_workspace.resize(clpt_wavefront_workspace_bytes(paths));
-            St.wf_max_paths = paths;
-        }
-    }
-    St.last_engine = wavefront ? 2 : 1;
+    // Engine: 1 = every lane walks its own leaf's triangles; 2 = warp-cooperative leaves
+    // (render_kernel.cu); 0 = chosen from the tree at CLSetMeshes.
+    St.last_engine = St.engine != 0 ? St.engine : St.auto_engine;
+    if (St.last_engine == 2) F.flags |= CLPT_F_COOP;
 
     // Claim direction (megakernel): decided from the previous frame's per-row cost under
     // the same image, sharding and parameters.  $CLPT_ROW_ORDER=0 turns it off.
     int order_rows = 0;
-    if (!wavefront) {
+    {
         const char *e = getenv("CLPT_ROW_ORDER");
         if (!(e && atoi(e) == 0)) order_rows = clpt_render_block_rows(F);
         // the bookkeeping (a memset and a small copy, ~15 us) is only worth it on frames long
@@ -525,15 +523,8 @@ void clpt_state_launch_frame(int width, int height) {
     }
     if (p2p) dist_barrier(); // every rank has finished with (reading) the previous frame
     CU(cudaEventRecord(St.ev_start, St.stream));
-    if (wavefront) {
-        const int n = clpt_launch_wavefront(St.scene, F, St.wf_workspace.ptr, St.wf_max_paths,
-                                            St.prop.multiProcessorCount, St.stream);
-        if (n < 0) FATAL("wavefront workspace too small");
-        St.last_launches += n;
-    } else {
-        clpt_launch_render(St.scene, F, St.prop.multiProcessorCount, St.stream);
-        St.last_launches++;
-    }
+    clpt_launch_render(St.scene, F, St.prop.multiProcessorCount, St.stream);
+    St.last_launches++;
     CU(cudaGetLastError());
     CU(cudaEventRecord(St.ev_stop, St.stream));
     if (order_rows > 0) {
@@ -655,8 +646,6 @@ void CLTerminate(void) {
     St.dist_word.release();
     St.dist_xchg.release();
     St.l2_flush.release();
-    St.wf_workspace.release();
-    St.wf_max_paths = 0;
     g_packed.nodes.release();
     g_packed.leaves.release();
     g_packed.tri.release();
@@ -699,7 +688,21 @@ void CLSetMeshes(kd *models) {
     require_init("CLSetMeshes");
     if (models == nullptr || list_size(models) / sizeof(kd) == 0) return; // src/CLState.c:126-129
     kd m = models[0];                                                     // models[0] only, :130
-    release_host_kd();
+    // The reference never frees on a re-set (src/CLState.c:124-131 overwrites State.kd), so calling
+    // CLSetMeshes again with the SAME kd -- an in-place updated scene, or simply a repeat -- is legal
+    // there.  The previously adopted lists are released only when they are different lists.
+    // A previously adopted list is released only if the new kd does not carry it again.
+    if (St.owns_kd) {
+        const void *incoming[5] = { m.node_vec, m.tri_indices, m.vert_vec, m.norm_vec, m.tri_vec };
+        void *held[5] = { St.host_kd.node_vec, St.host_kd.tri_indices, St.host_kd.vert_vec, St.host_kd.norm_vec,
+                          St.host_kd.tri_vec };
+        for (void *old : held) {
+            bool again = false;
+            for (const void *in : incoming) again |= (old == in);
+            if (old && !again) delete_list(old);
+        }
+        St.owns_kd = false;
+    }
     St.host_kd = m;
     St.owns_kd = true;
     upload_scene(m.node_vec, list_size(m.node_vec), m.tri_indices, list_size(m.tri_indices), m.tri_vec,
@@ -747,7 +750,7 @@ void CLSetRenderParams(int mode, int depth, int spp, unsigned int seed, int flag
 }
 
 void CLSetEngine(int engine) {
-    if (engine < 0 || engine > 2) FATAL("CLSetEngine: 0 auto, 1 megakernel, 2 wavefront");
+    if (engine < 0 || engine > 2) FATAL("CLSetEngine: 0 auto, 1 lane-per-ray leaves, 2 warp-cooperative leaves");
     St.engine = engine;
 }
 
@@ -883,6 +886,10 @@ void CLSetTileShard(int rank, int nranks, int tile_rows) {
     require_init("CLSetTileShard");
     if (nranks < 1 || rank < 0 || rank >= nranks || tile_rows < 4 || (tile_rows % 4) != 0)
         FATAL("CLSetTileShard: need 0 <= rank < nranks and tile_rows a positive multiple of 4");
+    // "sharding without a communicator": with a live communicator the gather buffers and the
+    // peer mappings are sized for ITS rank count, so the shard has to agree with it
+    if (St.comm && nranks != St.comm_ranks)
+        FATAL("CLSetTileShard: nranks differs from the live communicator's (CLDistShutdown first, or use CLDistInit)");
     p2p_teardown(); // under the sharding the mappings were made for
     St.rank = rank;
     St.nranks = nranks;

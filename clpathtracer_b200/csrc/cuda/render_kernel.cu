@@ -104,8 +104,76 @@ __device__ __forceinline__ V3 trace_sample(const ClptScene &S, const ClptFrame &
     return mk(fadd(fmul(k, col.x), str), fadd(fmul(k, col.y), str), fadd(fmul(k, col.z), str));
 }
 
+// The same sample with the warp-cooperative traversal (engine 2): every lane of the warp
+// calls this, `active` says whether it has a sample; the bounce loop is uniform across
+// the warp (lanes meet after every ray, as they do in trace_sample) so that finished
+// lanes keep helping with the fat leaves of the others.
 template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(256, CLPT_MIN_BLOCKS)
+__device__ __forceinline__ V3 trace_sample_coop(const ClptScene &S, const ClptFrame &F, int x, int y, unsigned pixel,
+                                                unsigned sample, bool active, bool aov, Counters &cn) {
+    const unsigned FULL = 0xffffffffu;
+    V3 o = mk(0.0f, 0.0f, 0.0f), d = mk(1.0f, 0.0f, 0.0f);
+    if (active) primary_ray(F, x, y, pixel, sample, o, d);
+    int depth = F.depth;
+    if (MODE == 0) depth = depth > 0 ? 1 : 0;
+    bool alive = active && depth > 0;
+    V3 col = mk(0.0f, 0.0f, 0.0f), T = mk(1.0f, 1.0f, 1.0f); // mode C: col is the radiance sum
+    float str = 1.0f;
+    for (int seg = 0; seg < depth; seg++) {
+        if (!__any_sync(FULL, alive)) break;
+        const Hit h = closest_hit_coop<COUNT>(S, o, d, alive, F.max_leaf_visits, cn);
+        if (!alive) continue;
+        if (seg == 0 && aov) write_aov<COUNT>(S, F, h, o, d, x, y);
+        if (h.ref < 0) {
+            if (MODE == 2) col = vadd(col, T);
+            alive = false;
+            continue;
+        }
+        const V3 nrm = hit_normal<COUNT>(S, h, o, d, cn);
+        if (MODE == 2) {
+            float al[3] = { 0.5f, 0.5f, 0.5f }, em[3] = { 0.0f, 0.0f, 0.0f };
+            int kind = 0;
+            if (S.n_materials > 0) {
+                int m = S.tri_material ? __ldg(S.tri_material + __float_as_int(__ldg(&S.tri[3 * (size_t)h.ref].w))) : 0;
+                if (m < 0 || m >= S.n_materials) m = 0;
+                const ClptMaterial *mp = S.materials + m;
+                al[0] = mp->albedo[0]; al[1] = mp->albedo[1]; al[2] = mp->albedo[2];
+                em[0] = mp->emission[0]; em[1] = mp->emission[1]; em[2] = mp->emission[2];
+                kind = mp->kind;
+            }
+            col = vadd(col, mk(fmul(T.x, em[0]), fmul(T.y, em[1]), fmul(T.z, em[2])));
+            T = mk(fmul(T.x, al[0]), fmul(T.y, al[1]), fmul(T.z, al[2]));
+            const V3 hp = vadd(o, vscale(d, h.t));
+            const V3 nd = kind == 1 ? vnormalize(vsub(d, vscale(nrm, fmul(2.0f, vdot(d, nrm)))))
+                                    : cosine_dir(nrm, pixel, sample, (unsigned)seg, F.seed);
+            o = vadd(hp, vscale(nd, 0.0001f));
+            d = nd;
+            continue;
+        }
+        const V3 nc = mk(fdiv(fadd(nrm.x, 1.0f), 2.0f), fdiv(fadd(nrm.y, 1.0f), 2.0f),
+                         fdiv(fadd(nrm.z, 1.0f), 2.0f));
+        if (MODE == 0) { // the `return` at :396
+            col = nc;
+            str = 0.0f; // marks "colour is final"
+            alive = false;
+            continue;
+        }
+        V3 no = vadd(o, vscale(d, h.t));
+        const V3 nd = vnormalize(vsub(d, vscale(nrm, fmul(2.0f, vdot(d, nrm)))));
+        no = vadd(no, vscale(nd, 0.0001f));
+        col = vadd(vscale(col, fsub(1.0f, str)), vscale(nc, str));
+        str = fmul(str, 0.2f);
+        o = no;
+        d = nd;
+    }
+    if (MODE == 2) return col;
+    if (MODE == 0 && str == 0.0f) return col;
+    const float k = fsub(1.0f, str); // :421
+    return mk(fadd(fmul(k, col.x), str), fadd(fmul(k, col.y), str), fadd(fmul(k, col.z), str));
+}
+
+template <int MODE, bool COUNT, bool COOP>
+__global__ void __launch_bounds__(256, COOP ? CLPT_COOP_MIN_BLOCKS : CLPT_MIN_BLOCKS)
 render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptFrame F) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int log2_s = F.log2_sample_lanes, s_lanes = 1 << log2_s;
@@ -159,7 +227,17 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
         for (int base = 0; base < spp; base += s_lanes) {
             const int s = base + sslot;
             V3 colour = mk(0.0f, 0.0f, 0.0f);
-            if (valid && s < spp) {
+            if (valid && s == 0 && F.aov_prim != nullptr && F.depth <= 0) {
+                // nothing is traced: the AOVs say "miss" instead of keeping the previous frame's
+                Hit none;
+                none.ref = -1;
+                none.t = 0.0f;
+                write_aov<COUNT>(S, F, none, mk(0.0f, 0.0f, 0.0f), mk(0.0f, 0.0f, 0.0f), x, y);
+            }
+            if (COOP) {
+                colour = trace_sample_coop<MODE, COUNT>(S, F, x, y, pixel, F.sample_base + (unsigned)s,
+                                                        valid && s < spp, s == 0 && F.aov_prim != nullptr, cn);
+            } else if (valid && s < spp) {
                 colour = trace_sample<MODE, COUNT>(S, F, x, y, pixel, F.sample_base + (unsigned)s,
                                                    s == 0 && F.aov_prim != nullptr, cn);
             }
@@ -235,10 +313,13 @@ __global__ void normalise_kernel(const float4 *__restrict__ src, float4 *__restr
 
 template <int MODE>
 void launch_mode(const ClptScene &scene, const ClptFrame &frame, unsigned grid, cudaStream_t stream) {
+    const bool coop = (frame.flags & CLPT_F_COOP) != 0;
     if (frame.flags & CLPT_F_COUNTERS) {
-        render_kernel<MODE, true><<<grid, 256, 0, stream>>>(scene, frame);
+        if (coop) render_kernel<MODE, true, true><<<grid, 256, 0, stream>>>(scene, frame);
+        else render_kernel<MODE, true, false><<<grid, 256, 0, stream>>>(scene, frame);
     } else {
-        render_kernel<MODE, false><<<grid, 256, 0, stream>>>(scene, frame);
+        if (coop) render_kernel<MODE, false, true><<<grid, 256, 0, stream>>>(scene, frame);
+        else render_kernel<MODE, false, false><<<grid, 256, 0, stream>>>(scene, frame);
     }
 }
 
@@ -262,7 +343,7 @@ void clpt_launch_render(const ClptScene &scene, const ClptFrame &frame_in, int s
     frame.blocks_x = (int)bx;
     frame.n_warp_tiles = (int)(bx * by * 8u);
     // persistent grid: enough blocks to fill every SM, never more than there are tiles
-    unsigned grid = (unsigned)sm_count * CLPT_MIN_BLOCKS;
+    unsigned grid = (unsigned)sm_count * ((frame.flags & CLPT_F_COOP) ? CLPT_COOP_MIN_BLOCKS : CLPT_MIN_BLOCKS);
     if (grid > bx * by) grid = bx * by;
     cudaMemsetAsync(frame.work_counter, 0, sizeof(unsigned), stream);
     switch (frame.mode) {
@@ -291,5 +372,5 @@ void clpt_launch_normalise(const float4 *src, float4 *dst, size_t n, cudaStream_
 }
 
 const void *clpt_render_kernel_symbol(void) {
-    return reinterpret_cast<const void *>(&render_kernel<0, false>);
+    return reinterpret_cast<const void *>(&render_kernel<0, false, false>);
 }

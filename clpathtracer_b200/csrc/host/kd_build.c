@@ -94,6 +94,20 @@ arena_thread(void) {
 #endif
 }
 
+/* Team size of the build's parallel regions: every thread owns one arena slot, so a
+ * host with more hardware threads than slots must not start more (threads t and
+ * t + ARENA_THREADS would otherwise share one unsynchronised bump pointer). */
+static int
+arena_team(void) {
+#ifdef _OPENMP
+    extern int omp_get_max_threads(void);
+    int n = omp_get_max_threads();
+    return n < 1 ? 1 : (n > ARENA_THREADS ? ARENA_THREADS : n);
+#else
+    return 1;
+#endif
+}
+
 static void *
 arena_alloc(size_t bytes) {
     bytes = (bytes + 15u) & ~(size_t)15u;
@@ -962,7 +976,8 @@ build_tree(cl_int3 *tris, Vector3 *verts, Vector3 *norms, const char *path,
 
     const double t1 = kd_now_ms();
     bnode *top = NULL;
-#pragma omp parallel
+    const int team = arena_team();
+#pragma omp parallel num_threads(team)
 #pragma omp single
     top = sah ? build_cell_sah(root, bmin.s, bmax.s, sah->max_depth, sah)
               : build_cell(root, bmin.s, bmax.s, depth, nbins);
@@ -972,12 +987,12 @@ build_tree(cl_int3 *tris, Vector3 *verts, Vector3 *norms, const char *path,
     emitter em;
     em.nodes = init_list(nnodes, sizeof(kdnode));
     em.refs = init_list(nrefs, sizeof(int));
-#pragma omp parallel
+#pragma omp parallel num_threads(team)
 #pragma omp single
     emit_preorder(&em, top, 0, 0);
     const double t3 = kd_now_ms();
     int links[6] = { -1, -1, -1, -1, -1, -1 };
-#pragma omp parallel
+#pragma omp parallel num_threads(team)
 #pragma omp single
     link_cells(em.nodes, 0, links, sah != NULL);
     if (timing) {

@@ -60,7 +60,10 @@ void CLSetObjects(Object *vec_objects, size_t size);
 /* Take models[0] (models is a list.c vector of kd; an empty vector is a
  * no-op), re-pack its node array / tri_indices / tris / verts / norms into the
  * device layout (DESIGN.md "data layout in HBM") and upload it.  Ownership of
- * models[0]'s five lists passes to the library.  Replaces src/CLState.c:124-202. */
+ * models[0]'s five lists passes to the library.  A later CLSetMeshes frees the
+ * lists adopted before EXCEPT those the new kd carries again (same pointer), so
+ * calling it again with the same kd after an in-place update is legal, as it is
+ * in the reference (which never frees on a re-set).  Replaces src/CLState.c:124-202. */
 void CLSetMeshes(kd *models);
 
 /* Release the current render target.  Replaces src/CLState.c:42-45. */
@@ -114,9 +117,13 @@ void CLSetMaterials(const CLMaterial *materials, size_t material_bytes,
  * samples per pixel per frame, RNG seed, CLPT_FLAG_* */
 void CLSetRenderParams(int mode, int depth, int spp, unsigned int seed, int flags);
 void CLSetMaxLeafVisits(int cap);          /* rope-hop cap per ray; default 4096 */
-/* Execution engine: 0 = automatic, 1 = megakernel (one thread runs a whole path),
- * 2 = wavefront (generate / trace / shade / resolve passes over ray queues in HBM).
- * Both produce the same bits; the choice is about speed only. */
+/* Execution engine: 1 = every lane walks the triangle run of its own leaf; 2 = the
+ * lanes of a warp stay in one traversal loop and share the triangle runs of fat
+ * leaves (>= 8 triangles: 32 triangles per step, ordered reduction) -- made for
+ * trees from the reference's own builder, whose DEPTH 15 cap (src/kd_tree.c:8-9)
+ * leaves ~56 triangles per leaf at 1M triangles; 0 = automatic: chosen per tree at
+ * CLSetMeshes (2 when most triangle slots sit in fat leaves).  Both produce the same
+ * bits; the choice is about speed only. */
 void CLSetEngine(int engine);
 int CLLastEngine(void);                    /* engine the last CLExecute used: 1 or 2 */
 void CLCreateImageHeadless(int width, int height); /* float4 target, zeroed */

@@ -157,13 +157,143 @@ size_t refcl_kernel_source_bytes(void) { return (size_t)(_binary_kernel_cl_end -
         return 2;                                                  \
     }
 
+/* ---- the bounce code of the reference, made runnable (mode B pin) ----------
+ *
+ * As shipped, trace_ray returns at src/kernel.cl:396-397 and the mirror bounce
+ * after that `return` (:399-417) is dead; it is also a self-recursion (:406),
+ * which OpenCL C forbids and the device stack does not survive.  To let the
+ * VENDOR compiler execute exactly that code, the source is rewritten as TEXT:
+ * trace_ray (:296-422) is cloned `depth` times, each clone is the reference's
+ * function character for character except that
+ *   - it has its own name,
+ *   - the early `return convert_color((normal + 1) / 2) ... ;` statement is
+ *     removed (so :399-417 runs), and
+ *   - the recursive call names the next clone instead of itself.
+ * The last clone is the function AS SHIPPED (early return kept; it is entered
+ * with depth 0 and falls through to `return (1-str)*col + str;`, :421).  The
+ * depth literal `2` in render (:468) becomes `depth`.  No arithmetic, no
+ * operand order and no constant is touched.  Returns a malloc'd string, or
+ * NULL (what is set) when the expected text is not found. */
+static char *find_in(char *hay, const char *needle) { return hay ? strstr(hay, needle) : NULL; }
+
+static void replace_once(char **text, const char *needle, const char *with, const char **what) {
+    char *at = find_in(*text, needle);
+    if (!at) {
+        if (*text) *what = needle;
+        free(*text);
+        *text = NULL;
+        return;
+    }
+    size_t head = (size_t)(at - *text), nl = strlen(needle), wl = strlen(with), tl = strlen(*text);
+    char *out = malloc(tl - nl + wl + 1);
+    memcpy(out, *text, head);
+    memcpy(out + head, with, wl);
+    memcpy(out + head + wl, at + nl, tl - head - nl + 1);
+    free(*text);
+    *text = out;
+}
+
+static char *dup_range(const char *a, const char *b) {
+    char *r = malloc((size_t)(b - a) + 1);
+    memcpy(r, a, (size_t)(b - a));
+    r[b - a] = '\0';
+    return r;
+}
+
+static char *bounce_source(const char *src, size_t srclen, int depth, const char **what) {
+    static const char fn_head[] = "color\ntrace_ray(Ray r,";
+    static const char fn_next[] = "kernel void";
+    static const char early_a[] = "return convert_color((normal + 1) / 2)/*";
+    static const char early_b[] = "*/;";
+    static const char call[] = "return trace_ray(newRay,";
+    static const char literal[] = "kd_tree,\n                    2,\n";
+    char *all = dup_range(src, src + srclen);
+    char *fs = strstr(all, fn_head), *fe = fs ? strstr(fs, fn_next) : NULL;
+    if (!fs || !fe) {
+        *what = "trace_ray definition";
+        free(all);
+        return NULL;
+    }
+    char *fn = dup_range(fs, fe);
+    size_t cap = srclen + (size_t)(depth + 2) * (strlen(fn) + 64) + 64, len = 0;
+    char *out = malloc(cap);
+    memcpy(out, all, (size_t)(fs - all));
+    len = (size_t)(fs - all);
+    /* clones, deepest first so that every callee is defined before its caller */
+    for (int level = depth; level >= 0; level--) {
+        char name[32], callee[64], defn[64];
+        char *c = dup_range(fn, fn + strlen(fn));
+        if (level == 0) snprintf(name, sizeof name, "trace_ray");
+        else snprintf(name, sizeof name, "trace_ray_%d", level);
+        snprintf(defn, sizeof defn, "color\n%s(Ray r,", name);
+        replace_once(&c, fn_head, defn, what);
+        if (level == depth) { /* as shipped; its dead self-call keeps naming itself */
+            snprintf(callee, sizeof callee, "return %s(newRay,", name);
+            replace_once(&c, call, callee, what);
+        } else {
+            char *a = find_in(c, early_a), *b = a ? strstr(a, early_b) : NULL;
+            if (!a || !b) {
+                *what = "early return statement";
+                free(c);
+                c = NULL;
+            } else {
+                memmove(a, b + sizeof early_b - 1, strlen(b + sizeof early_b - 1) + 1);
+                snprintf(callee, sizeof callee, "return trace_ray_%d(newRay,", level + 1);
+                replace_once(&c, call, callee, what);
+            }
+        }
+        if (!c) {
+            free(out);
+            free(fn);
+            free(all);
+            return NULL;
+        }
+        memcpy(out + len, c, strlen(c));
+        len += strlen(c);
+        free(c);
+    }
+    size_t tail = strlen(fe);
+    memcpy(out + len, fe, tail + 1);
+    free(fn);
+    free(all);
+    char lit[64];
+    snprintf(lit, sizeof lit, "kd_tree,\n                    %d,\n", depth);
+    /* the literal sits in render, after every clone */
+    char *render_at = strstr(out + len, literal);
+    if (!render_at) {
+        *what = "depth literal in render";
+        free(out);
+        return NULL;
+    }
+    char *headpart = dup_range(out, render_at), *rest = dup_range(render_at, out + len + tail);
+    free(out);
+    replace_once(&rest, literal, lit, what);
+    if (!rest) {
+        free(headpart);
+        return NULL;
+    }
+    out = malloc(strlen(headpart) + strlen(rest) + 1);
+    strcpy(out, headpart);
+    strcat(out, rest);
+    free(headpart);
+    free(rest);
+    return out;
+}
+
+/* The rewritten source the last bounce render compiled (for inspection/tests); caller frees. */
+char *refcl_bounce_source(int depth) {
+    const char *what = NULL;
+    return bounce_source(_binary_kernel_cl_start, refcl_kernel_source_bytes(), depth, &what);
+}
+void refcl_free(void *p) { free(p); }
+
 /* Render one frame with the reference kernel, exactly the launch of
  * src/CLState.c:204-219.  rgba_out: w*h*4 floats.  kernel_ms: device time of the
  * NDRange from event profiling, best of `repeats`. */
-int refcl_render(const void *nodes, size_t node_bytes, const int *tri_indices, size_t tri_index_bytes,
-                 const void *tris, size_t tri_bytes, const void *verts, size_t vert_bytes, const void *norms,
-                 size_t norm_bytes, const float cam[16], int w, int h, int repeats, float *rgba_out,
-                 double *kernel_ms, char *log, int loglen) {
+int refcl_render_depth(const void *nodes, size_t node_bytes, const int *tri_indices, size_t tri_index_bytes,
+                       const void *tris, size_t tri_bytes, const void *verts, size_t vert_bytes, const void *norms,
+                       size_t norm_bytes, const float cam[16], int w, int h, int repeats, int bounce_depth,
+                       float *rgba_out, double *kernel_ms, char *log, int loglen) {
     cl_platform_id plat;
     cl_device_id dev;
     cl_int e;
@@ -186,7 +316,20 @@ int refcl_render(const void *nodes, size_t node_bytes, const int *tri_indices, s
     static const char *labels[] = { "", "-cl-std=CL2.0", "-cl-std=CL3.0",
                                     "source patched in memory: mul() parameter `const matrix M` -> `global const vec4 *M`" };
     static const char *options[] = { NULL, "-cl-std=CL2.0", "-cl-std=CL3.0", NULL };
-    const size_t reflen = refcl_kernel_source_bytes();
+    /* bounce_depth <= 0: the source as shipped.  Otherwise the text rewrite above. */
+    const char *refsrc = _binary_kernel_cl_start;
+    size_t reflen = refcl_kernel_source_bytes();
+    char *bounce = NULL;
+    if (bounce_depth > 0) {
+        const char *what = NULL;
+        bounce = bounce_source(refsrc, reflen, bounce_depth, &what);
+        if (!bounce) {
+            snprintf(log, loglen, "bounce rewrite: `%s` not found in kernel.cl", what ? what : "?");
+            return 3;
+        }
+        refsrc = bounce;
+        reflen = strlen(bounce);
+    }
     static const char needle[] = "mul(const matrix M, vec3 X)";
     static const char patch[] = "mul(global const vec4 *M, vec3 X)";
     char *patched = NULL;
@@ -194,20 +337,20 @@ int refcl_render(const void *nodes, size_t node_bytes, const int *tri_indices, s
     int used = -1;
     char first_log[4096] = "";
     for (int i = 0; i < 4 && used < 0; i++) {
-        const char *src = _binary_kernel_cl_start;
+        const char *src = refsrc;
         size_t srclen = reflen;
         if (i == 3) {
             const char *at = NULL;
             for (size_t p = 0; p + sizeof needle - 1 <= reflen; p++) {
-                if (memcmp(_binary_kernel_cl_start + p, needle, sizeof needle - 1) == 0) {
-                    at = _binary_kernel_cl_start + p;
+                if (memcmp(refsrc + p, needle, sizeof needle - 1) == 0) {
+                    at = refsrc + p;
                     break;
                 }
             }
             if (!at) break;
-            size_t head = (size_t)(at - _binary_kernel_cl_start);
+            size_t head = (size_t)(at - refsrc);
             patched = malloc(reflen + sizeof patch);
-            memcpy(patched, _binary_kernel_cl_start, head);
+            memcpy(patched, refsrc, head);
             memcpy(patched + head, patch, sizeof patch - 1);
             memcpy(patched + head + sizeof patch - 1, at + sizeof needle - 1, reflen - head - (sizeof needle - 1));
             src = patched;
@@ -229,9 +372,11 @@ int refcl_render(const void *nodes, size_t node_bytes, const int *tri_indices, s
                            e, first_log);
         if (off < loglen - 1) cl.GetProgramBuildInfo(prog, dev, CL_PROGRAM_BUILD_LOG, (size_t)(loglen - off - 1), log + off, &n);
         free(patched);
+        free(bounce);
         return 2;
     }
     free(patched);
+    free(bounce);
     g_build_options = labels[used];
     cl_kernel k = cl.CreateKernel(prog, "render", &e); /* KERNEL_NAME, src/main.c:7 */
     CHECK(e, "clCreateKernel");
@@ -294,4 +439,13 @@ int refcl_render(const void *nodes, size_t node_bytes, const int *tri_indices, s
     cl.ReleaseContext(ctx);
     if (log && loglen) log[0] = '\0';
     return 0;
+}
+
+/* The kernel as shipped (first-hit normal colour). */
+int refcl_render(const void *nodes, size_t node_bytes, const int *tri_indices, size_t tri_index_bytes,
+                 const void *tris, size_t tri_bytes, const void *verts, size_t vert_bytes, const void *norms,
+                 size_t norm_bytes, const float cam[16], int w, int h, int repeats, float *rgba_out,
+                 double *kernel_ms, char *log, int loglen) {
+    return refcl_render_depth(nodes, node_bytes, tri_indices, tri_index_bytes, tris, tri_bytes, verts, vert_bytes,
+                              norms, norm_bytes, cam, w, h, repeats, 0, rgba_out, kernel_ms, log, loglen);
 }

@@ -48,6 +48,8 @@
  * spp > 1 or flags&ORACLE_JITTER adds sub-pixel jitter from Philox4x32-10;
  * with spp == 1 and no jitter, ray generation is exactly the reference's.
  */
+#define _GNU_SOURCE
+#include <sched.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -104,6 +106,8 @@ typedef struct oracle_params {
     float *t_hit;
     float *uv;        /* 2 floats per pixel */
     float *normal;    /* 3 floats per pixel */
+    float *path_edge; /* min over the hits of sample 0's path of min(u, v, |1-u-v|): how close the
+                       * path came to a triangle edge (classifies tie-break mismatches); 2 = no hit */
     /* work counters, summed over all rays: rays, splits, leaves, tri tests,
      * vn-shaded hits, rays stopped by the cap */
     uint64_t counters[6];
@@ -331,8 +335,15 @@ found:;
     return normalize3(d);
 }
 
+static inline void note_edge(float *edge, const hit_t *h) {
+    if (!edge || !h->did_hit) return;
+    float w = fabsf(1.0f - h->u - h->v), m = h->u < h->v ? h->u : h->v;
+    if (w < m) m = w;
+    if (m < *edge) *edge = m;
+}
+
 static f3 shade_sample(const oracle_params *P, ray_t r, uint32_t pixel, uint32_t sample,
-                       hit_t *first, uint64_t *cnt) {
+                       hit_t *first, float *edge, uint64_t *cnt) {
     int depth = P->depth;
     if (P->mode == 0) depth = depth > 0 ? 1 : 0;
     if (P->mode == 2) {
@@ -340,6 +351,7 @@ static f3 shade_sample(const oracle_params *P, ray_t r, uint32_t pixel, uint32_t
         for (int seg = 0; seg < depth; seg++) {
             hit_t h = closest_hit(P, &r, cnt);
             if (seg == 0 && first) *first = h;
+            note_edge(edge, &h);
             if (!h.did_hit) { L = add3(L, T); return L; }
             int m = P->tri_material ? P->tri_material[h.prim] : 0;
             if (m < 0 || m >= P->n_materials) m = 0;
@@ -367,6 +379,7 @@ static f3 shade_sample(const oracle_params *P, ray_t r, uint32_t pixel, uint32_t
     for (; depth > 0; depth--) {
         hit_t h = closest_hit(P, &r, cnt);
         if (first) { *first = h; first = NULL; }
+        note_edge(edge, &h);
         if (!h.did_hit) break;
         f3 nc = v3((h.normal.x + 1) / 2, (h.normal.y + 1) / 2, (h.normal.z + 1) / 2);
         if (P->mode == 0) return nc; /* kernel.cl:396 */
@@ -401,6 +414,7 @@ int oracle_render(oracle_params *P) {
                 f3 origin = v3(M[2] / M[14], M[6] / M[14], M[10] / M[14]);
                 f3 acc = v3(0, 0, 0);
                 hit_t first;
+                float edge = 2.0f;
                 memset(&first, 0, sizeof(first));
                 first.prim = -1;
                 for (int s = 0; s < spp; s++) {
@@ -417,7 +431,7 @@ int oracle_render(oracle_params *P) {
                     f3 fcp = unproject(M, v3(fx, fy, 1));
                     f3 dir = normalize3(sub3(fcp, ncp));
                     ray_t r = make_ray(origin, dir);
-                    f3 c = shade_sample(P, r, pixel, sample, s == 0 ? &first : NULL, cnt);
+                    f3 c = shade_sample(P, r, pixel, sample, s == 0 ? &first : NULL, s == 0 ? &edge : NULL, cnt);
                     acc = add3(acc, c);
                 }
                 size_t o = (size_t)y * (size_t)W + (size_t)x;
@@ -435,6 +449,7 @@ int oracle_render(oracle_params *P) {
                 if (P->prim_id) P->prim_id[o] = first.did_hit ? first.prim : -1;
                 if (P->t_hit) P->t_hit[o] = first.did_hit ? first.t : 0.0f;
                 if (P->uv) { P->uv[2 * o] = first.u; P->uv[2 * o + 1] = first.v; }
+                if (P->path_edge) P->path_edge[o] = edge;
                 if (P->normal) {
                     P->normal[3 * o] = first.normal.x;
                     P->normal[3 * o + 1] = first.normal.y;
@@ -456,4 +471,11 @@ int oracle_num_threads(void) {
 #else
     return 1;
 #endif
+}
+/* Cores this process may run on (the affinity mask), whatever OMP_NUM_THREADS says:
+ * torchrun exports OMP_NUM_THREADS=1, which must not shrink the CPU baseline. */
+int oracle_host_cores(void) {
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) return CPU_COUNT(&set);
+    return oracle_num_threads();
 }

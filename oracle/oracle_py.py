@@ -34,7 +34,7 @@ class OracleParams(C.Structure):
         ("materials", C.c_void_p), ("tri_material", C.c_void_p),
         ("n_materials", C.c_int32), ("reserved", C.c_int32),
         ("rgba", C.c_void_p), ("prim_id", C.c_void_p), ("t_hit", C.c_void_p),
-        ("uv", C.c_void_p), ("normal", C.c_void_p),
+        ("uv", C.c_void_p), ("normal", C.c_void_p), ("path_edge", C.c_void_p),
         ("counters", C.c_uint64 * 6),
     ]
 
@@ -57,6 +57,7 @@ def oracle() -> C.CDLL:
         L.oracle_render.argtypes = [C.POINTER(OracleParams)]
         L.oracle_sizeof_params.restype = C.c_size_t
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_host_cores.restype = C.c_int
         L.oracle_philox.restype = None
         L.oracle_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         assert L.oracle_sizeof_params() == C.sizeof(OracleParams)
@@ -141,6 +142,8 @@ def render(scene, cam: np.ndarray, width: int, height: int, mode: int = 0, depth
         out["normal"] = np.zeros((height, width, 3), dtype=np.float32)
         P.prim_id, P.t_hit = out["prim"].ctypes.data, out["t"].ctypes.data
         P.uv, P.normal = out["uv"].ctypes.data, out["normal"].ctypes.data
+        out["path_edge"] = np.full((height, width), 2.0, dtype=np.float32)
+        P.path_edge = out["path_edge"].ctypes.data
     rc = L.oracle_render(C.byref(P))
     assert rc == 0
     out["counters"] = dict(zip(COUNTER_NAMES, [int(x) for x in P.counters]))
@@ -169,6 +172,12 @@ def _ref_kernel():
         L.refcl_render.restype = C.c_int
         L.refcl_render.argtypes = [C.c_void_p, C.c_size_t] * 5 + [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                                                  C.POINTER(C.c_double), C.c_char_p, C.c_int]
+        L.refcl_render_depth.restype = C.c_int
+        L.refcl_render_depth.argtypes = [C.c_void_p, C.c_size_t] * 5 + [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                                       C.c_void_p, C.POINTER(C.c_double), C.c_char_p,
+                                                                       C.c_int]
+        L.refcl_bounce_source.restype, L.refcl_bounce_source.argtypes = C.c_void_p, [C.c_int]
+        L.refcl_free.restype, L.refcl_free.argtypes = None, [C.c_void_p]
         L.refcl_build_options.restype = C.c_char_p
         _refk = L
     return _refk
@@ -183,20 +192,37 @@ def ref_kernel_available() -> tuple[bool, str]:
     return rc == 0, msg.value.decode(errors="replace")
 
 
-def ref_kernel_render(scene, cam: np.ndarray, width: int, height: int, repeats: int = 1):
-    """One frame of the UNMODIFIED reference kernel (as shipped: first-hit normal
-    colour).  Returns (rgba float32[h,w,4], kernel_ms)."""
+def ref_kernel_bounce_source(depth: int) -> str:
+    """The text the vendor compiler is given for a bounce render (cl_harness.c:
+    trace_ray cloned `depth` times with the early return removed)."""
+    L = _ref_kernel()
+    p = L.refcl_bounce_source(depth)
+    if not p:
+        raise RuntimeError("bounce rewrite failed: kernel.cl does not have the expected text")
+    try:
+        return C.string_at(p).decode()
+    finally:
+        L.refcl_free(p)
+
+
+def ref_kernel_render(scene, cam: np.ndarray, width: int, height: int, repeats: int = 1, bounce_depth: int = 0):
+    """One frame of the reference kernel.  bounce_depth 0: UNMODIFIED, as shipped
+    (first-hit normal colour).  bounce_depth D >= 1: the reference's dead mirror
+    bounce (src/kernel.cl:399-417) made runnable by the textual clone in
+    cl_harness.c, trace depth D (the literal at :468 is 2).
+    Returns (rgba float32[h,w,4], kernel_ms)."""
     L = _ref_kernel()
     camf = np.ascontiguousarray(cam, dtype=np.float32).reshape(16)
     out = np.zeros((height, width, 4), dtype=np.float32)
     ms = C.c_double(0)
     log = C.create_string_buffer(16384)
     norms = scene.norms if len(scene.norms) else None
-    rc = L.refcl_render(scene.nodes.ctypes.data, scene.nodes.nbytes, scene.tri_indices.ctypes.data,
-                        scene.tri_indices.nbytes, scene.tris.ctypes.data, scene.tris.nbytes,
-                        scene.verts.ctypes.data, scene.verts.nbytes,
-                        None if norms is None else norms.ctypes.data, 0 if norms is None else norms.nbytes,
-                        camf.ctypes.data, width, height, repeats, out.ctypes.data, C.byref(ms), log, 16384)
+    rc = L.refcl_render_depth(scene.nodes.ctypes.data, scene.nodes.nbytes, scene.tri_indices.ctypes.data,
+                              scene.tri_indices.nbytes, scene.tris.ctypes.data, scene.tris.nbytes,
+                              scene.verts.ctypes.data, scene.verts.nbytes,
+                              None if norms is None else norms.ctypes.data, 0 if norms is None else norms.nbytes,
+                              camf.ctypes.data, width, height, repeats, bounce_depth, out.ctypes.data,
+                              C.byref(ms), log, 16384)
     if rc != 0:
         raise RuntimeError("reference kernel run failed: " + log.value.decode(errors="replace"))
     return out, ms.value

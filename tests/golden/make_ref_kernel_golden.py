@@ -4,7 +4,13 @@ Runs the reference's own, unmodified src/kernel.cl (linked as a blob into
 oracle/_ref/libref_kernel.so by `make -C oracle ref`, see oracle/cl_harness.c)
 through the OpenCL ICD of the box's NVIDIA driver, on the deterministic scenes
 below, and stores the float4 frames it writes.  The kernel as shipped returns
-the first hit's normal colour (src/kernel.cl:395-397), white on a miss.
+the first hit's normal colour (src/kernel.cl:395-397), white on a miss; those
+frames are stored under the case name.  Under `<case>_d2` and `<case>_d5` it
+stores the frames of the reference's mirror bounce (src/kernel.cl:399-417) at
+trace depth 2 (the literal at :468) and 5 (the bench depth), executed by the
+same vendor compiler from the textual clone oracle/cl_harness.c makes
+(bounce_source: the early return removed, the recursion unrolled into named
+copies, nothing else).
 
     gpurun -- 'python tests/golden/make_ref_kernel_golden.py gpurun_out/ref_kernel_golden.npz'
 then copy the file to tests/golden/.
@@ -46,6 +52,12 @@ def main(out_path):
         arrays[name] = rgba[..., :3].copy()
         meta["cases"][name] = {"kernel_ms": ms, "hit_fraction": float((rgba[..., :3] != 1.0).any(axis=-1).mean())}
         print(name, meta["cases"][name])
+        for d in (2, 5):
+            rgba, ms = op.ref_kernel_render(scene, cam, W, H, bounce_depth=d)
+            assert np.all(rgba[..., 3] == 1.0)
+            arrays[f"{name}_d{d}"] = rgba[..., :3].copy()
+            meta["cases"][f"{name}_d{d}"] = {"kernel_ms": ms, "build": op.ref_kernel_build_options()}
+            print(name, d, meta["cases"][f"{name}_d{d}"])
     arrays["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
     np.savez_compressed(out_path, **arrays)
 

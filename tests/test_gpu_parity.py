@@ -92,70 +92,72 @@ def test_sah_trees_bit_exact(clpt, oracle, renderer, scene_cache, name, camera, 
     _assert_bit_equal(img, ref["rgba"], "rgba")
 
 
-WF_CASES = [
-    # scene, sah, camera, w, h, mode, depth, spp, flags
-    ("hf22n", False, "canonical", 320, 240, 1, 5, 1, 0),
-    ("hf22", True, "canonical", 333, 197, 1, 3, 6, 1),       # spp not a power of two, jitter
-    ("cornell", True, "cornell", 320, 240, 1, 4, 4, 1),
-    ("soup3000", False, "cornell", 256, 256, 1, 4, 2, 1),
-    ("hf224", True, "canonical", 480, 270, 1, 5, 8, 1),
-    ("hf22n", False, "canonical", 200, 150, 0, 2, 3, 1),       # mode A through the wavefront passes
-    ("hf22n", False, "canonical", 200, 150, 1, 1, 1, 0),       # a single segment
-    ("hf22n", False, "canonical", 64, 48, 1, 0, 1, 0),         # depth 0: nothing is traced
+COOP_CASES = [
+    # scene, tree, camera, w, h, mode, depth, spp, flags
+    ("hf224", False, "canonical", 480, 270, 0, 2, 1, 0),      # reference tree, ~21 triangles per leaf, as shipped
+    ("hf224", False, "canonical", 480, 270, 1, 5, 1, 0),      # mirror bounces
+    ("hf224", False, "canonical", 333, 197, 1, 3, 6, 1),      # spp not a power of two, jitter, odd size
+    ("hf22n", 6, "canonical", 320, 240, 1, 4, 4, 1),          # a very shallow tree: 30+ triangles per leaf, vn shading
+    ("soup3000", 5, "cornell", 256, 256, 1, 4, 2, 1),         # incoherent, fat leaves
+    ("cornell", False, "cornell", 320, 240, 2, 4, 8, 1),      # path mode through the cooperative loop
+    ("hf22n", False, "canonical", 200, 150, 1, 1, 1, 0),      # thin leaves only: the per-lane branch of engine 2
+    ("hf22n", False, "canonical", 64, 48, 1, 0, 1, 0),        # depth 0: nothing is traced, AOVs say miss
 ]
 
 
-@pytest.mark.parametrize("name,sah,camera,w,h,mode,depth,spp,flags", WF_CASES)
-def test_wavefront_engine_bit_exact(clpt, oracle, renderer, scene_cache, name, sah, camera, w, h, mode, depth, spp,
-                                    flags):
-    """The wavefront engine (ray queues in HBM, persistent trace kernel with lane
-    refill) produces the same bits as the oracle -- and therefore as the megakernel."""
-    scene, _ = scene_cache(name, sah=sah)
+@pytest.mark.parametrize("name,tree,camera,w,h,mode,depth,spp,flags", COOP_CASES)
+def test_cooperative_engine_bit_exact(clpt, oracle, renderer, scene_cache, name, tree, camera, w, h, mode, depth, spp,
+                                      flags):
+    """Engine 2 (the lanes of a warp share the triangle runs of fat leaves; ordered
+    reduction for the later-triangle-wins tie rule, src/kernel.cl:344) produces the same
+    bits as the oracle and as engine 1, work counters included."""
+    from clpathtracer_b200 import scenes
+
+    if isinstance(tree, bool):
+        scene, _ = scene_cache(name, sah=tree)
+    else:  # the reference heuristic stopped at a small depth: fat leaves on a small scene
+        gen = {"hf22n": lambda: scenes.heightfield(22, True), "soup3000": lambda: scenes.soup(3000)}[name]
+        scene = clpt.build_kd(*gen(), depth=tree)
+    assert scene.stats()["max_leaf_tris"] >= 8 or name in ("hf22n", "cornell")
     cam = _cam(clpt, camera, h)
     L = clpt.lib()
+    kw = dict(mode=mode, depth=depth, spp=spp, seed=5)
+    okw = {}
+    if mode == 2:  # one diffuse material with a little emission (set_meshes keeps the material table)
+        grey = np.array([[0.7, 0.6, 0.5, 0, 0.1, 0.1, 0.2, 0]], dtype=np.float32)
+        renderer.set_materials(grey, None)
+        okw["materials"] = grey
     try:
         L.CLSetEngine(2)
-        img, prim, t, uv = _render_gpu(renderer, scene, cam, w, h, mode=mode, depth=depth, spp=spp, seed=5,
-                                       flags=flags | clpt.FLAG_COUNTERS)
-        assert L.CLLastEngine() == 2 and L.CLLastLaunchCount() >= 3
+        img, prim, t, uv = _render_gpu(renderer, scene, cam, w, h, flags=flags | clpt.FLAG_COUNTERS, **kw)
+        assert L.CLLastEngine() == 2
         got_counters = renderer.counters()
+        plain = _render_gpu(renderer, scene, cam, w, h, flags=flags, **kw)[0]
         L.CLSetEngine(1)
-        mega = _render_gpu(renderer, scene, cam, w, h, mode=mode, depth=depth, spp=spp, seed=5, flags=flags)[0]
+        lane = _render_gpu(renderer, scene, cam, w, h, flags=flags, **kw)[0]
         assert L.CLLastEngine() == 1
     finally:
         L.CLSetEngine(0)
-    ref = oracle.render(scene, cam, w, h, mode=mode, depth=depth, spp=spp, seed=5, flags=flags)
+    ref = oracle.render(scene, cam, w, h, flags=flags, **kw, **okw)
     assert np.array_equal(prim, ref["prim"])
     _assert_bit_equal(t, ref["t"], "t")
     _assert_bit_equal(uv, ref["uv"], "uv")
     _assert_bit_equal(img, ref["rgba"], "rgba")
-    _assert_bit_equal(img, mega, "wavefront vs megakernel")
+    _assert_bit_equal(plain, ref["rgba"], "rgba (uninstrumented kernel)")
+    _assert_bit_equal(img, lane, "cooperative vs lane-per-ray")
     assert got_counters == ref["counters"]
 
 
-def test_wavefront_chunking_and_sharding(clpt, oracle, renderer, scene_cache, monkeypatch):
-    """A workspace smaller than the frame (several chunks) and row-tile sharding."""
-    scene, _ = scene_cache("hf22n")
-    w, h = 200, 150
-    cam = _cam(clpt, "canonical", h)
-    full = oracle.render(scene, cam, w, h, mode=1, depth=3, spp=4, seed=9, flags=clpt.FLAG_JITTER)["rgba"]
+def test_engine_is_chosen_per_tree(clpt, renderer, scene_cache):
+    """Automatic engine: cooperative for trees whose triangles sit in fat leaves (the
+    reference builder at 100k triangles), lane-per-ray for SAH trees."""
     L = clpt.lib()
-    monkeypatch.setenv("CLPT_WF_MAX_PATHS", str(w * 4 * 7))  # 7 rows per chunk
-    try:
-        L.CLSetEngine(2)
-        img = _render_gpu(renderer, scene, cam, w, h, aov=False, mode=1, depth=3, spp=4, seed=9,
-                          flags=clpt.FLAG_JITTER)[0]
-        _assert_bit_equal(img, full, "chunked")
-        assert L.CLLastLaunchCount() > 20
-        for rank in range(3):
-            renderer.create_image(w, h)
-            L.CLSetTileShard(rank, 3, 8)
-            renderer.execute()
-            rows = np.array([y for y in range(h) if (y // 8) % 3 == rank], dtype=int)
-            _assert_bit_equal(renderer.read_image()[rows], full[rows], f"rank {rank}")
-    finally:
-        L.CLSetTileShard(0, 1, 8)
-        L.CLSetEngine(0)
+    L.CLSetEngine(0)
+    cam = _cam(clpt, "canonical", 48)
+    for sah, want in ((False, 2), (True, 1)):
+        scene, _ = scene_cache("hf224", sah=sah)
+        _render_gpu(renderer, scene, cam, 64, 48, aov=False, mode=0, depth=2)
+        assert L.CLLastEngine() == want
 
 
 @pytest.mark.parametrize("depth_tree", [8, 20, 24])
