@@ -60,7 +60,12 @@ def parse_args():
                     help="0 auto, 1 megakernel, 2 wavefront")
     ap.add_argument("--tile-rows", type=int, default=8)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--readback", default="rgba8", choices=["rgba8", "float4"],
+                    help="format of the end-to-end read-back: the reference's RGBA8 texture format, or the float4 frame")
+    ap.add_argument("--readback-sync", action="store_true", help="blocking read-back instead of the pipelined one")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true",
+                    help="skip the word-for-word comparison of the rendered frame with the oracle")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the baseline sample")
     ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c4", "c5"],
                     help="BASELINE.json configs[0..3]; c3 (the default) is the one the metric is quoted on")
@@ -169,26 +174,79 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_baseline(a, scene, cam, target_seconds):
-    """The oracle port on this box's host cores, on a bounded sample of the same
-    workload: the same frame at fewer samples per pixel."""
+def host_cores():
+    """Cores this process may run on.  torchrun exports OMP_NUM_THREADS=1; the CPU arms
+    use the affinity mask instead so that they run on all host cores at every N."""
     from oracle import oracle_py as op
 
-    cores = op.oracle().oracle_num_threads()
-    kw = dict(mode=1, depth=a.depth, seed=a.seed, flags=op.FLAG_JITTER, aov=False)
+    return int(op.oracle().oracle_host_cores())
+
+
+def oracle_mode(a):
+    return {"normal": 0, "mirror": 1, "path": 2}[a.mode]
+
+
+def oracle_flags(a):
+    from oracle import oracle_py as op
+
+    return 0 if a.no_jitter else op.FLAG_JITTER
+
+
+def oracle_check_and_baseline(a, scene, cam, gpu_frame, target_seconds, want_baseline):
+    """One run of the oracle port (all host cores) serves two purposes: it is the
+    `cpu_baseline` sample, and its frame is compared WORD FOR WORD with the frame the
+    GPU path just rendered with the timed parameters (`parity`).  The whole frame at
+    full spp when that fits the time budget (the default workload: ~9 s on 16 cores),
+    else the whole frame at fewer spp for the baseline and a band of rows at full spp
+    for the comparison."""
+    import hashlib
+
+    from oracle import oracle_py as op
+
+    cores = host_cores()
+    kw = dict(mode=oracle_mode(a), depth=a.depth, seed=a.seed, flags=oracle_flags(a), aov=False, threads=cores)
     t0 = time.time()
-    r = op.render(scene, cam, a.width, a.height, spp=1, **kw)
+    r1 = op.render(scene, cam, a.width, a.height, spp=1, **kw)
     t1 = time.time() - t0
-    spp, rays, secs = 1, r["counters"]["rays"], t1
-    more = int(min(a.spp, target_seconds / max(t1, 1e-3)))
-    if more >= 2:
-        t0 = time.time()
-        r = op.render(scene, cam, a.width, a.height, spp=more, **kw)
-        secs, rays, spp = time.time() - t0, r["counters"]["rays"], more
-    return {"value": round(rays / secs / 1e6, 4), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"same scene/camera/depth, full {a.width}x{a.height} frame at {spp} of {a.spp} spp "
-                      f"({rays} rays in {secs:.1f} s)",
-            "ms_per_frame_at_full_spp": round(secs / spp * a.spp * 1e3, 1)}
+    full = a.spp == 1 or t1 * a.spp <= 2.0 * target_seconds
+    baseline, parity = None, {"checked": False}
+    if full:
+        if a.spp == 1:
+            ref, secs = r1, t1
+        else:
+            t0 = time.time()
+            ref = op.render(scene, cam, a.width, a.height, spp=a.spp, **kw)
+            secs = time.time() - t0
+        rays, spp, rows = ref["counters"]["rays"], a.spp, (0, a.height)
+    else:
+        spp = max(1, int(min(a.spp, target_seconds / max(t1, 1e-3))))
+        if want_baseline and spp > 1:
+            t0 = time.time()
+            rb = op.render(scene, cam, a.width, a.height, spp=spp, **kw)
+            secs, rays = time.time() - t0, rb["counters"]["rays"]
+        else:
+            secs, rays, spp = t1, r1["counters"]["rays"], 1
+        band = max(8, int(a.height * target_seconds / max(t1 * a.spp, 1e-3)) // 8 * 8)
+        rows = (max(0, a.height // 2 - band // 2), min(a.height, a.height // 2 - band // 2 + band))
+        ref = op.render(scene, cam, a.width, a.height, spp=a.spp, rows=rows, **kw)
+    if want_baseline:
+        baseline = {"value": round(rays / secs / 1e6, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"same scene/camera/depth, full {a.width}x{a.height} frame at {spp} of {a.spp} spp "
+                              f"({rays} rays in {secs:.1f} s)",
+                    "ms_per_frame_at_full_spp": round(secs / spp * a.spp * 1e3, 1)}
+    if gpu_frame is not None:
+        want = ref["rgba"][rows[0]:rows[1]]
+        got = gpu_frame[rows[0]:rows[1]]
+        differ = int(np.count_nonzero(np.ascontiguousarray(got).view(np.uint32) != np.ascontiguousarray(want).view(np.uint32)))
+        parity = {"checked": True, "words_differ": differ, "words": int(want.size), "rows": list(rows),
+                  "oracle_sha256": hashlib.sha256(np.ascontiguousarray(want).tobytes()).hexdigest(),
+                  "oracle": "oracle/oracle_kernel.c (CPU restatement of src/kernel.cl, -ffp-contract=off) on the same "
+                            "scene, tree, camera, seed, spp and depth as the timed frames",
+                  "reference_pin": "mirror bounce pinned at depth 2 and 5, 1 spp, by the reference's own kernel.cl run "
+                                   "through the vendor OpenCL compiler (tests/test_reference_kernel.py, "
+                                   "tests/golden/ref_kernel_stats_r02.json); jitter and multi-spp accumulation have no "
+                                   "reference behaviour (extension, defined by the oracle)"}
+    return baseline, parity
 
 
 def run_reference(a):
@@ -201,9 +259,9 @@ def run_reference(a):
     from oracle import oracle_py as op
 
     scene, cam, info = make_scene(a)
-    cores = op.oracle().oracle_num_threads()
+    cores = host_cores()
     ref_spp = min(8, a.spp)
-    kw = dict(mode=1, depth=a.depth, spp=ref_spp, flags=op.FLAG_JITTER, aov=False)
+    kw = dict(mode=oracle_mode(a), depth=a.depth, spp=ref_spp, flags=oracle_flags(a), aov=False, threads=cores)
     for w in range(a.warmup):
         op.render(scene, cam, a.width, a.height, seed=a.seed, sample_base=w * ref_spp, **kw)
     rays, t0 = 0, time.time()
@@ -211,7 +269,27 @@ def run_reference(a):
         rays += op.render(scene, cam, a.width, a.height, seed=a.seed, sample_base=k * ref_spp, **kw)["counters"]["rays"]
     secs = time.time() - t0
     value = rays / secs / 1e6
-    sample = f"each step = the full {a.width}x{a.height} frame at {ref_spp} of {a.spp} spp, depth {a.depth}"
+    sample = (f"each step = the full {a.width}x{a.height} frame at {ref_spp} of {a.spp} spp, depth {a.depth}; the "
+              f"reference's algorithm (CPU port of src/kernel.cl, oracle/oracle_kernel.c) walking THIS repository's "
+              f"kd-tree ({workload_config(a)['kd_builder']}) -- the reference as shipped cannot render this workload "
+              f"(no bounces, samples or accumulation) and its own DEPTH-15 tree is slower, see reference_tree")
+    # the same port on the tree the reference's own builder makes (src/kd_tree.c, DEPTH 15 / 25 bins)
+    import clpathtracer_b200 as cl
+    from clpathtracer_b200 import scenes
+
+    ref_tree = None
+    if 2 * a.grid * a.grid <= 1_100_000:
+        t0 = time.time()
+        own = cl.build_kd(*scenes.heightfield(a.grid, False))
+        t_build = time.time() - t0
+        t0 = time.time()
+        rr = op.render(own, cam, a.width, a.height, seed=a.seed, **dict(kw, spp=1))
+        dt = time.time() - t0
+        ref_tree = {"value": round(rr["counters"]["rays"] / dt / 1e6, 4), "unit": UNIT, "cores": cores,
+                    "sample": f"one full frame at 1 of {a.spp} spp on the reference builder's own tree "
+                              f"(DEPTH 15, 25 bins; {own.stats()['leaf_tri_refs'] / max(own.stats()['leaves'] - own.stats()['empty_leaves'], 1):.1f} "
+                              f"triangles per non-empty leaf), {rr['counters']['rays']} rays in {dt:.1f} s",
+                    "kd_build_s": round(t_build, 2)}
     emit({
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(secs / a.steps * 1e3, 2),
@@ -219,6 +297,7 @@ def run_reference(a):
         "config": workload_config(a),
         "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "reference_tree": ref_tree,
         "scene": info,
     })
 
@@ -424,17 +503,49 @@ def main():
     launches = a.steps * L.CLLastLaunchCount()
 
     # ---- timed: end to end through the C ABI with host buffers ----
-    host_frame = torch.empty((a.height, a.width, 4), dtype=torch.float32).pin_memory()
-    host_np = host_frame.numpy()
+    # Every step: camera matrix host -> device, CLExecute, and the step's result -- ONE frame --
+    # device -> pinned host memory.  The frame is delivered in the reference's render-target
+    # format (RGBA8, src/GLHandler.c:177-185) unless --readback float4, through the pipelined
+    # read-back (CLReadImageAsync: frame k travels while frame k+1 renders; every frame has
+    # landed before the clock stops).  Across GPUs the frame is assembled on every rank and
+    # read back by rank 0, the rank that owns the host buffer; a progressive frame lives in the
+    # ranks' slabs, so its read-back is collective and every rank takes part.
+    host_dtype = torch.uint8 if a.readback == "rgba8" else torch.float32
+    host_frames = [torch.empty((a.height, a.width, 4), dtype=host_dtype).pin_memory() for _ in range(2)]
+    host_np = [t.numpy() for t in host_frames]
     cam_host = np.ascontiguousarray(cam, dtype=np.float32)
+    reader = rank == 0 or (a.progressive and world > 1)
     barrier()
     e2e_t0 = time.time()
-    for _ in range(a.steps):
+    for k in range(a.steps):
         r.set_camera_matrix(cam_host)   # 64 B host -> device (rides in the launch parameters)
         r.execute()
-        r.read_image(host_np)           # float4 frame device -> pinned host
+        if reader:
+            if a.readback_sync:
+                (r.read_image_rgba8 if a.readback == "rgba8" else r.read_image)(host_np[k & 1])
+            else:
+                r.read_image_async(host_np[k & 1])
+                r.read_wait(1)          # frame k-1 has landed; frame k travels during the next step
+    if reader:
+        r.read_wait(0)
     barrier()
     e2e_s = time.time() - e2e_t0
+    d2h_bytes = a.width * a.height * (4 if a.readback == "rgba8" else 16)
+
+    # ---- self-check frame: the timed parameters, read back once more (outside every timed region) ----
+    import hashlib
+
+    if a.progressive:
+        L.CLResetAccumulation()
+    r.execute()
+    check_frame = r.read_image().copy()
+    my_sha = hashlib.sha256(check_frame.tobytes()).hexdigest()
+    shas = [my_sha]
+    if world > 1:
+        mine = torch.tensor(list(bytes.fromhex(my_sha)), dtype=torch.uint8, device="cuda")
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        shas = [bytes(x.cpu().tolist()).hex() for x in every]
 
     t = torch.tensor([sum(step_ms), sum(kern_ms), e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -470,7 +581,13 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(a),
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": 64,
-                    "d2h_bytes_per_step": a.width * a.height * 16, "ms_per_step": round(e2e_ms / a.steps, 4)},
+                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": round(e2e_ms / a.steps, 4),
+                    "readback": {"format": a.readback, "pipelined": not a.readback_sync,
+                                 "api": "CLReadImageAsync + CLReadImageWait" if not a.readback_sync else
+                                        ("CLReadImageRGBA8" if a.readback == "rgba8" else "CLReadImage"),
+                                 "readers": world if (a.progressive and world > 1) else 1,
+                                 "note": "one frame per step reaches pinned host memory inside the timed region; "
+                                         "RGBA8 is the reference's render-target format"}},
             "gpu_launches": launches,
             "per_rank_kernel_ms": per_rank_kernel_ms,
             "clocks": clocks,
@@ -491,10 +608,21 @@ def main():
             "device": L.CLDeviceName().decode(), "scene": info,
             "engine": {1: "megakernel", 2: "wavefront"}[L.CLLastEngine()],
         }
-        if world == 1 and not a.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(a, scene, cam, a.cpu_seconds)
+        want_baseline = world == 1 and not a.no_cpu_baseline
+        if want_baseline or not a.no_parity_check:
+            baseline, parity = oracle_check_and_baseline(a, scene, cam, None if a.no_parity_check else check_frame,
+                                                         a.cpu_seconds, want_baseline)
         else:
-            out["cpu_baseline"] = None
+            baseline, parity = None, {"checked": False}
+        # every rank holds the whole frame: one sha per rank, to be compared with each other and,
+        # across runs, with the N=1 line's
+        parity["frame_sha256"] = shas[0]
+        parity["frame_sha256_per_rank"] = shas
+        parity["ranks_agree"] = len(set(shas)) == 1
+        if parity.get("checked") and parity["rows"] == [0, a.height]:
+            parity["frame_equals_oracle"] = parity["words_differ"] == 0 and parity["oracle_sha256"] == shas[0]
+        out["cpu_baseline"] = baseline
+        out["parity"] = parity
         emit(out)
     if world > 1:
         L.CLDistShutdown()

@@ -37,6 +37,7 @@ the plane, b = axis, c[0:2] = children.  For a leaf: a = first slot in
 tri_indices, b = triangle count, c[0:6] = ropes."""
 
 MODE_NORMAL, MODE_MIRROR, MODE_PATH = 0, 1, 2
+READ_FLOAT4, READ_RGBA8 = 0, 1
 FLAG_JITTER, FLAG_ACCUMULATE, FLAG_COUNTERS = 1, 2, 4
 
 
@@ -112,6 +113,7 @@ def lib() -> C.CDLL:
         "CLSelectDevice": (None, [i]), "CLSetRenderParams": (None, [i, i, i, u, i]),
         "CLSetMaxLeafVisits": (None, [i]), "CLSetEngine": (None, [i]), "CLLastEngine": (i, []), "CLCreateImageHeadless": (None, [i, i]),
         "CLResetAccumulation": (None, []), "CLReadImage": (None, [vp, sz]),
+        "CLReadImageRGBA8": (None, [vp, sz]), "CLReadImageAsync": (None, [vp, sz, i]), "CLReadImageWait": (None, [i]),
         "CLEnableAOV": (None, [i]), "CLReadAOV": (None, [vp, vp, vp]),
         "CLGetCounters": (None, [vp]), "CLLastKernelMs": (f, []), "CLLastLaunchCount": (i, []),
         "CLEventRecord": (None, [i]), "CLEventElapsedMs": (f, [i, i]), "CLFlushL2": (None, []),
@@ -329,6 +331,22 @@ class Renderer:
             out = np.empty((self.height, self.width, 4), dtype=np.float32)
         self.L.CLReadImage(out.ctypes.data, out.nbytes)
         return out
+
+    def read_image_rgba8(self, out: np.ndarray | None = None) -> np.ndarray:
+        """The frame as RGBA8 UNORM texels, the reference's render-target format."""
+        if out is None:
+            out = np.empty((self.height, self.width, 4), dtype=np.uint8)
+        self.L.CLReadImageRGBA8(out.ctypes.data, out.nbytes)
+        return out
+
+    def read_image_async(self, out: np.ndarray) -> None:
+        """Pipelined read-back into `out` (float32 -> float4 frame, uint8 -> RGBA8); `out`
+        must stay alive and untouched until read_wait() says the read has landed."""
+        fmt = READ_RGBA8 if out.dtype == np.uint8 else READ_FLOAT4
+        self.L.CLReadImageAsync(out.ctypes.data, out.nbytes, fmt)
+
+    def read_wait(self, leave_pending: int = 0) -> None:
+        self.L.CLReadImageWait(int(leave_pending))
 
     def read_aov(self):
         n = self.width * self.height

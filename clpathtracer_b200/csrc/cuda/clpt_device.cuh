@@ -91,6 +91,13 @@ struct ClptFrame {
     int blocks_x, n_warp_tiles;   // filled in by clpt_launch_render
 };
 
+#ifdef __CUDACC__
+// float in [0,1] -> UNORM8, round to nearest even, NaN -> 0: a UNORM8 image write.
+__device__ __forceinline__ unsigned clpt_to_unorm8(float v) {
+    return (unsigned)__float2int_rn(__saturatef(v) * 255.0f);
+}
+#endif
+
 enum { CLPT_F_JITTER = 1, CLPT_F_ACCUMULATE = 2, CLPT_F_COUNTERS = 4, CLPT_F_REVERSE = 0x100 /* internal */,
        CLPT_F_COOP = 0x200 /* internal: warp-cooperative leaves (engine 2) */ };
 
@@ -101,4 +108,12 @@ void clpt_launch_deinterleave(const float4 *gathered, float4 *image, int width, 
                               int nranks, int tile_rows, int slab_rows, cudaStream_t stream);
 void clpt_launch_fill(float4 *dst, size_t n, float value, cudaStream_t stream);
 void clpt_launch_normalise(const float4 *src, float4 *dst, size_t n, cudaStream_t stream);
+struct ClptFlagPeers {
+    unsigned int *flags[CLPT_MAX_PEERS]; // rank r's barrier words (peer mappings; this rank's own at [rank])
+};
+// Barrier across the ranks of a node through peer-mapped words: word [src * 8] of rank dst's
+// array is written by src only.  Epochs only grow.
+void clpt_launch_flag_barrier(const ClptFlagPeers &peers, int rank, int nranks, unsigned int epoch,
+                              cudaStream_t stream);
+void clpt_launch_pack_rgba8(const float4 *src, uchar4 *dst, size_t n, cudaStream_t stream);
 const void *clpt_render_kernel_symbol(void);

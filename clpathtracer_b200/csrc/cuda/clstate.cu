@@ -167,6 +167,17 @@ struct {
     float last_kernel_ms = 0;
     int last_launches = 0;
     DevBuf<unsigned char> l2_flush;
+    // Read-back pipeline (CLReadImageAsync): two device staging buffers; the frame is copied or
+    // packed into one on the library's stream, and travels to the host on a second stream while
+    // the next frame renders.
+    cudaStream_t copy_stream = nullptr;
+    struct ReadSlot {
+        DevBuf<unsigned char> staging;
+        cudaEvent_t ready = nullptr, done = nullptr;
+        bool in_flight = false;
+        unsigned long long ticket = 0;
+    } rd[2];
+    unsigned long long rd_issued = 0;
     int engine = 0;      // 0 auto, 1 lane-per-ray leaves, 2 warp-cooperative leaves
     int auto_engine = 1; // what "auto" means for the current tree (decided in upload_scene)
     int last_engine = 1;
@@ -178,6 +189,10 @@ struct {
     bool p2p = false;
     int p2p_self = -1; // this rank's slot in peer_image (its own frame, not a mapping)
     float4 *peer_image[CLPT_MAX_PEERS] = {};
+    // flag-word barrier: every rank owns one word per peer (32 B apart) in `flags`, mapped by all
+    DevBuf<unsigned int> bar_flags;
+    unsigned int *peer_flags[CLPT_MAX_PEERS] = {};
+    unsigned int flag_epoch = 0;
     DevBuf<int> dist_word;           // operand of the barrier all-reduce
     DevBuf<unsigned char> dist_xchg; // handle exchange staging
 } St;
@@ -317,6 +332,17 @@ void dist_barrier() {
     NC(g_nccl.AllReduce(St.dist_word.ptr, St.dist_word.ptr + 1, 1, ncclInt, ncclSum, St.comm, St.stream));
 }
 
+// Barrier over the peer-mapped flag words (direct placement only): a one-block kernel on the
+// library's stream stores this frame's epoch into its word on every rank and spins until every
+// rank's epoch has arrived in its own words -- a few microseconds over NVLink, against ~20 for a
+// one-word ncclAllReduce, twice per frame.
+void flag_barrier() {
+    ClptFlagPeers peers;
+    for (int r = 0; r < CLPT_MAX_PEERS; r++) peers.flags[r] = St.peer_flags[r];
+    clpt_launch_flag_barrier(peers, St.rank, St.nranks, ++St.flag_epoch, St.stream);
+    CU(cudaGetLastError());
+}
+
 int dist_min(int v) {
     dist_word_ready();
     int out = 0;
@@ -338,6 +364,10 @@ void p2p_close_mappings() {
             }
         }
         St.peer_image[r] = nullptr;
+        if (St.peer_flags[r] && r != St.p2p_self) {
+            if (cudaIpcCloseMemHandle(St.peer_flags[r]) != cudaSuccess) (void)cudaGetLastError();
+        }
+        St.peer_flags[r] = nullptr;
     }
     St.p2p_self = -1;
 }
@@ -363,14 +393,23 @@ void p2p_setup() {
         if (atoi(e) == 0) return; // has to be set on every rank alike
     }
     struct Slot {
-        cudaIpcMemHandle_t handle;
+        cudaIpcMemHandle_t handle, flags_handle;
         int ok;
-        int pad[15];
+        int pad[31];
     };
-    static_assert(sizeof(Slot) == 128, "exchange slot is 128 bytes");
+    static_assert(sizeof(Slot) == 256, "exchange slot is 256 bytes");
     Slot mine;
     memset(&mine, 0, sizeof(mine));
-    mine.ok = cudaIpcGetMemHandle(&mine.handle, St.image.ptr) == cudaSuccess ? 1 : 0;
+    // the barrier words: zeroed here, before the exchange below orders every rank's zeroing
+    // ahead of any rank's first signal
+    // (a whole 2 MiB block of its own: IPC handles cover the driver's underlying allocation)
+    St.bar_flags.resize((2u << 20) / sizeof(unsigned int));
+    CU(cudaMemsetAsync(St.bar_flags.ptr, 0, CLPT_MAX_PEERS * 8 * sizeof(unsigned int), St.stream));
+    St.flag_epoch = 0;
+    mine.ok = cudaIpcGetMemHandle(&mine.handle, St.image.ptr) == cudaSuccess &&
+                      cudaIpcGetMemHandle(&mine.flags_handle, St.bar_flags.ptr) == cudaSuccess
+                  ? 1
+                  : 0;
     if (!mine.ok) (void)cudaGetLastError();
     const size_t n = (size_t)St.nranks;
     St.dist_xchg.resize(sizeof(Slot) * (n + 1));
@@ -387,14 +426,22 @@ void p2p_setup() {
     for (size_t r = 0; ok && r < n; r++) {
         if ((int)r == St.rank) {
             St.peer_image[r] = St.image.ptr;
+            St.peer_flags[r] = St.bar_flags.ptr;
             continue;
         }
-        void *mapped = nullptr;
+        void *mapped = nullptr, *mapped_flags = nullptr;
         if (cudaIpcOpenMemHandle(&mapped, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
             (void)cudaGetLastError();
             ok = 0;
         } else {
             St.peer_image[r] = (float4 *)mapped;
+            if (cudaIpcOpenMemHandle(&mapped_flags, all[r].flags_handle, cudaIpcMemLazyEnablePeerAccess) !=
+                cudaSuccess) {
+                (void)cudaGetLastError();
+                ok = 0;
+            } else {
+                St.peer_flags[r] = (unsigned int *)mapped_flags;
+            }
         }
     }
     ok = dist_min(ok);
@@ -412,8 +459,11 @@ void p2p_setup() {
     }
 }
 
+void release_read_pipeline();
+
 void alloc_targets() {
     p2p_teardown();
+    release_read_pipeline();
     const size_t px = (size_t)St.width * St.height;
     St.image.resize(px);
     clpt_launch_fill(St.image.ptr, px, 0.0f, St.stream);
@@ -438,6 +488,110 @@ void alloc_targets() {
     St.sample_base = 0;
     CU(cudaStreamSynchronize(St.stream));
     p2p_setup();
+}
+
+// True when the ranks accumulate in their own slabs and nothing crosses GPUs per frame
+// ("Progressive accumulation: accumulate locally per rank; gather only
+// on display/readback").
+bool accumulates_locally() { return (St.flags & CLPT_FLAG_ACCUMULATE) && St.nranks > 1; }
+
+// The current frame as displayable float4 (rgb, 1) on the library's stream.  Replace mode: the
+// frame itself.  Progressive mode: sum / count into `scratch`; across GPUs the ranks' slabs are
+// gathered first (ncclAllGather + de-interleave), which makes the call COLLECTIVE in that case.
+const float4 *displayable_frame() {
+    const size_t px = (size_t)St.width * St.height;
+    if (!(St.flags & CLPT_FLAG_ACCUMULATE)) return St.image.ptr;
+    if (St.scratch.count != px) St.scratch.resize(px);
+    if (St.nranks > 1) {
+        const size_t slab_px = (size_t)slab_rows_for(St.height) * St.width;
+        if (St.gathered.count != slab_px * St.nranks) {
+            St.gathered.resize(slab_px * St.nranks);
+            CU(cudaMemsetAsync(St.gathered.ptr, 0, slab_px * St.nranks * sizeof(float4), St.stream));
+        }
+        if (St.comm) {
+            NC(g_nccl.AllGather(St.slab.ptr, St.gathered.ptr, slab_px * 4, ncclFloat, St.comm, St.stream));
+        } else { // sharded without a communicator: this rank's rows only
+            CU(cudaMemcpyAsync(St.gathered.ptr + slab_px * St.rank, St.slab.ptr, slab_px * sizeof(float4),
+                               cudaMemcpyDeviceToDevice, St.stream));
+        }
+        clpt_launch_deinterleave(St.gathered.ptr, St.scratch.ptr, St.width, St.height, St.nranks, St.tile_rows,
+                                 slab_rows_for(St.height), St.stream);
+        clpt_launch_normalise(St.scratch.ptr, St.scratch.ptr, px, St.stream);
+    } else {
+        clpt_launch_normalise(St.image.ptr, St.scratch.ptr, px, St.stream);
+    }
+    CU(cudaGetLastError());
+    return St.scratch.ptr;
+}
+
+size_t frame_bytes(int format) {
+    return (size_t)St.width * St.height * (format == CLPT_READ_RGBA8 ? sizeof(uchar4) : sizeof(float4));
+}
+
+void check_read(const char *who, size_t bytes, int format) {
+    require_init(who);
+    if (!St.have_image) {
+        fprintf(stderr, "%s: no render target\n", who);
+        exit(EXIT_FAILURE);
+    }
+    if (format != CLPT_READ_FLOAT4 && format != CLPT_READ_RGBA8) {
+        fprintf(stderr, "%s: format must be CLPT_READ_FLOAT4 or CLPT_READ_RGBA8\n", who);
+        exit(EXIT_FAILURE);
+    }
+    if (bytes != frame_bytes(format)) {
+        fprintf(stderr, "%s: %zu bytes given, the %dx%d %s frame is %zu\n", who, bytes, St.width, St.height,
+                format == CLPT_READ_RGBA8 ? "RGBA8" : "float4", frame_bytes(format));
+        exit(EXIT_FAILURE);
+    }
+}
+
+// Frame -> slot staging on the library's stream; staging -> host on the copy stream.
+void enqueue_read(void *dst, size_t bytes, int format) {
+    auto &slot = St.rd[St.rd_issued & 1];
+    if (!slot.ready) {
+        CU(cudaEventCreateWithFlags(&slot.ready, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&slot.done, cudaEventDisableTiming));
+    }
+    if (!St.copy_stream) CU(cudaStreamCreateWithFlags(&St.copy_stream, cudaStreamNonBlocking));
+    // the copy that last used this staging buffer must have drained before it is rewritten
+    if (slot.in_flight) CU(cudaStreamWaitEvent(St.stream, slot.done, 0));
+    const float4 *src = displayable_frame();
+    if (slot.staging.count < bytes) slot.staging.resize(bytes);
+    if (format == CLPT_READ_RGBA8) {
+        clpt_launch_pack_rgba8(src, reinterpret_cast<uchar4 *>(slot.staging.ptr), (size_t)St.width * St.height,
+                               St.stream);
+        CU(cudaGetLastError());
+    } else {
+        CU(cudaMemcpyAsync(slot.staging.ptr, src, bytes, cudaMemcpyDeviceToDevice, St.stream));
+    }
+    CU(cudaEventRecord(slot.ready, St.stream));
+    CU(cudaStreamWaitEvent(St.copy_stream, slot.ready, 0));
+    CU(cudaMemcpyAsync(dst, slot.staging.ptr, bytes, cudaMemcpyDeviceToHost, St.copy_stream));
+    CU(cudaEventRecord(slot.done, St.copy_stream));
+    slot.in_flight = true;
+    slot.ticket = ++St.rd_issued;
+}
+
+void wait_reads(unsigned long long leave_pending) {
+    // oldest first
+    for (int k = 0; k < 2; k++) {
+        auto &slot = St.rd[(St.rd_issued + k) & 1];
+        if (slot.in_flight && slot.ticket + leave_pending <= St.rd_issued) {
+            CU(cudaEventSynchronize(slot.done));
+            slot.in_flight = false;
+        }
+    }
+}
+
+void release_read_pipeline() {
+    wait_reads(0);
+    for (auto &slot : St.rd) {
+        slot.staging.release();
+        if (slot.ready) CU(cudaEventDestroy(slot.ready));
+        if (slot.done) CU(cudaEventDestroy(slot.done));
+        slot.ready = slot.done = nullptr;
+        slot.in_flight = false;
+    }
 }
 
 } // namespace
@@ -480,7 +634,8 @@ void clpt_state_launch_frame(int width, int height) {
     F.work_counter = St.work_counter.ptr;
     F.blocks_x = F.n_warp_tiles = 0;
     F.row_cost = nullptr;
-    const bool p2p = St.p2p && St.comm && St.nranks > 1;
+    const bool local_only = accumulates_locally(); // progressive across GPUs: nothing crosses GPUs per frame
+    const bool p2p = St.p2p && St.comm && St.nranks > 1 && !local_only;
     F.n_peer_images = p2p ? St.nranks : 0;
     for (int r = 0; r < CLPT_MAX_PEERS; r++) F.peer_image[r] = p2p ? St.peer_image[r] : nullptr;
     if (St.flags & CLPT_FLAG_COUNTERS) {
@@ -521,7 +676,7 @@ void clpt_state_launch_frame(int width, int height) {
         F.row_cost = St.row_cost.ptr;
         if (St.claim_reverse) F.flags |= CLPT_F_REVERSE;
     }
-    if (p2p) dist_barrier(); // every rank has finished with (reading) the previous frame
+    if (p2p) flag_barrier(); // every rank has finished with (reading) the previous frame
     CU(cudaEventRecord(St.ev_start, St.stream));
     clpt_launch_render(St.scene, F, St.prop.multiProcessorCount, St.stream);
     St.last_launches++;
@@ -533,7 +688,9 @@ void clpt_state_launch_frame(int width, int height) {
     }
 
     if (p2p) {
-        dist_barrier(); // every rank's pixels have landed in this rank's frame
+        flag_barrier(); // every rank's pixels have landed in this rank's frame
+    } else if (local_only) {
+        // the slab holds this rank's running sums; CLReadImage* gathers (displayable_frame)
     } else if (St.nranks > 1 && St.comm) {
         const size_t slab_px = (size_t)slab_rows_for(height) * width;
         if (St.gathered.count != slab_px * St.nranks) St.gathered.resize(slab_px * St.nranks);
@@ -557,7 +714,7 @@ void clpt_state_launch_frame(int width, int height) {
         St.last_launches++;
     }
     if (!St.headless && clpt_gl_registered()) {
-        clpt_gl_present(St.image.ptr, width, height, St.stream); // acquire/write/release, :207-218
+        clpt_gl_present(displayable_frame(), width, height, St.stream); // acquire/write/release, :207-218
         St.last_launches++;
     }
     CU(cudaStreamSynchronize(St.stream)); // clFinish, src/CLState.c:212
@@ -613,6 +770,9 @@ void CLTerminate(void) {
     if (!St.inited) return;
     release_host_kd(); // delete_kd(State.kd), src/CLState.c:223
     CU(cudaStreamSynchronize(St.stream));
+    release_read_pipeline();
+    if (St.copy_stream) CU(cudaStreamDestroy(St.copy_stream));
+    St.copy_stream = nullptr;
     p2p_teardown();
     if (St.comm) {
         NC(g_nccl.CommDestroy(St.comm));
@@ -645,6 +805,7 @@ void CLTerminate(void) {
     St.claim_reverse = false;
     St.dist_word.release();
     St.dist_xchg.release();
+    St.bar_flags.release();
     St.l2_flush.release();
     g_packed.nodes.release();
     g_packed.leaves.release();
@@ -765,6 +926,7 @@ void CLDeleteImage(void) {
     require_init("CLDeleteImage");
     if (!St.have_image) FATAL("CLDeleteImage: no render target"); // clReleaseMemObject(0) errors too
     p2p_teardown(); // collective: no rank frees a frame its peers still map
+    release_read_pipeline();
     if (clpt_gl_registered()) clpt_gl_unregister();
     St.image.release();
     St.slab.release();
@@ -809,23 +971,27 @@ void CLResetAccumulation(void) {
 void CLExecute(int width, int height) { clpt_state_launch_frame(width, height); }
 
 void CLReadImage(float *dst_rgba, size_t bytes) {
-    require_init("CLReadImage");
-    if (!St.have_image) FATAL("CLReadImage: no render target");
-    const size_t px = (size_t)St.width * St.height;
-    if (bytes != px * sizeof(float4)) {
-        fprintf(stderr, "CLReadImage: %zu bytes given, the %dx%d float4 frame is %zu\n", bytes, St.width,
-                St.height, px * sizeof(float4));
-        exit(EXIT_FAILURE);
-    }
-    const float4 *src = St.image.ptr;
-    if (St.flags & CLPT_FLAG_ACCUMULATE) {
-        if (St.scratch.count != px) St.scratch.resize(px);
-        clpt_launch_normalise(St.image.ptr, St.scratch.ptr, px, St.stream);
-        CU(cudaGetLastError());
-        src = St.scratch.ptr;
-    }
+    check_read("CLReadImage", bytes, CLPT_READ_FLOAT4);
+    wait_reads(0);
+    const float4 *src = displayable_frame();
     CU(cudaMemcpyAsync(dst_rgba, src, bytes, cudaMemcpyDeviceToHost, St.stream));
     CU(cudaStreamSynchronize(St.stream));
+}
+
+void CLReadImageRGBA8(unsigned char *dst_rgba8, size_t bytes) {
+    check_read("CLReadImageRGBA8", bytes, CLPT_READ_RGBA8);
+    enqueue_read(dst_rgba8, bytes, CLPT_READ_RGBA8);
+    wait_reads(0);
+}
+
+void CLReadImageAsync(void *dst, size_t bytes, int format) {
+    check_read("CLReadImageAsync", bytes, format);
+    enqueue_read(dst, bytes, format);
+}
+
+void CLReadImageWait(int leave_pending) {
+    require_init("CLReadImageWait");
+    wait_reads(leave_pending < 0 ? 0 : (unsigned long long)leave_pending);
 }
 
 void CLEnableAOV(int enable) {

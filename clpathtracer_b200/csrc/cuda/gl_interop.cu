@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include "CLHandler.h"
+#include "clpt_device.cuh"
 
 extern "C" cudaError_t cudaGraphicsGLRegisterImage(struct cudaGraphicsResource **resource, unsigned int image,
                                                    unsigned int target, unsigned int flags);
@@ -25,17 +26,12 @@ namespace {
 
 cudaGraphicsResource *g_resource = nullptr;
 
-__device__ __forceinline__ unsigned to_unorm8(float v) {
-    v = fminf(fmaxf(v, 0.0f), 1.0f);
-    return (unsigned)__float2int_rn(v * 255.0f); // round to nearest even, like a UNORM8 image write
-}
-
 __global__ void present_kernel(cudaSurfaceObject_t surf, const float4 *__restrict__ frame, int width, int height) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= width || y >= height) return;
     const float4 c = frame[(size_t)y * width + x];
-    const uchar4 texel = make_uchar4((unsigned char)to_unorm8(c.x), (unsigned char)to_unorm8(c.y),
-                                     (unsigned char)to_unorm8(c.z), (unsigned char)to_unorm8(c.w));
+    const uchar4 texel = make_uchar4((unsigned char)clpt_to_unorm8(c.x), (unsigned char)clpt_to_unorm8(c.y),
+                                     (unsigned char)clpt_to_unorm8(c.z), (unsigned char)clpt_to_unorm8(c.w));
     surf2Dwrite(texel, surf, x * (int)sizeof(uchar4), y);
 }
 

@@ -311,6 +311,34 @@ __global__ void normalise_kernel(const float4 *__restrict__ src, float4 *__restr
     }
 }
 
+// Displayable float4 frame -> RGBA8 UNORM texels, the format of the reference's render
+// target (src/GLHandler.c:177-185): what write_imagef does to a CL_UNORM_INT8 image,
+// clamp to [0,1], scale by 255, round to nearest even.
+__global__ void pack_rgba8_kernel(const float4 *__restrict__ src, uchar4 *__restrict__ dst, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 c = src[i];
+    dst[i] = make_uchar4((unsigned char)clpt_to_unorm8(c.x), (unsigned char)clpt_to_unorm8(c.y),
+                         (unsigned char)clpt_to_unorm8(c.z), (unsigned char)clpt_to_unorm8(c.w));
+}
+
+// One block, one thread per rank.  The stores of the kernels before this one on the stream
+// (pixels placed into the peers' frames) are ordered before the signal by the system-scope
+// fence + release store; the acquire load orders the peers' pixels before whatever follows.
+__global__ void flag_barrier_kernel(const __grid_constant__ ClptFlagPeers peers, int rank, int nranks,
+                                    unsigned int epoch) {
+    const int r = threadIdx.x;
+    if (r >= nranks) return;
+    __threadfence_system();
+    unsigned int *signal = peers.flags[r] + rank * 8;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(signal), "r"(epoch) : "memory");
+    const unsigned int *wait = peers.flags[rank] + r * 8;
+    unsigned int seen;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(wait) : "memory");
+    } while ((int)(seen - epoch) < 0);
+}
+
 template <int MODE>
 void launch_mode(const ClptScene &scene, const ClptFrame &frame, unsigned grid, cudaStream_t stream) {
     const bool coop = (frame.flags & CLPT_F_COOP) != 0;
@@ -369,6 +397,16 @@ void clpt_launch_fill(float4 *dst, size_t n, float value, cudaStream_t stream) {
 void clpt_launch_normalise(const float4 *src, float4 *dst, size_t n, cudaStream_t stream) {
     if (n == 0) return;
     normalise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, dst, n);
+}
+
+void clpt_launch_flag_barrier(const ClptFlagPeers &peers, int rank, int nranks, unsigned int epoch,
+                              cudaStream_t stream) {
+    flag_barrier_kernel<<<1, 32, 0, stream>>>(peers, rank, nranks, epoch);
+}
+
+void clpt_launch_pack_rgba8(const float4 *src, uchar4 *dst, size_t n, cudaStream_t stream) {
+    if (n == 0) return;
+    pack_rgba8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, dst, n);
 }
 
 const void *clpt_render_kernel_symbol(void) {

@@ -130,8 +130,23 @@ void CLCreateImageHeadless(int width, int height); /* float4 target, zeroed */
 void CLResetAccumulation(void);            /* zero the target and the sample counter */
 /* Blocking device->host copy of the whole float4 frame (bytes must be
  * width*height*16).  With CLPT_FLAG_ACCUMULATE the running sum is normalised
- * by the sample count on the way out. */
+ * by the sample count on the way out.  Across GPUs a progressive frame is
+ * accumulated in each rank's own rows and gathered here (ncclAllGather), which
+ * makes the CLReadImage* calls COLLECTIVE while CLPT_FLAG_ACCUMULATE is set and
+ * a communicator is live; in every other case only the calling rank pays. */
 void CLReadImage(float *dst_rgba, size_t bytes);
+/* The same frame as RGBA8 UNORM texels -- the format of the reference's render
+ * target (src/GLHandler.c:177-185; what write_imagef stores: clamp, x255, round to
+ * nearest even), 4 bytes per pixel (bytes must be width*height*4).  Blocking. */
+void CLReadImageRGBA8(unsigned char *dst_rgba8, size_t bytes);
+/* Pipelined read-back: the frame is snapshotted on the device in stream order and
+ * travels to `dst` on a second stream, so the next CLExecute overlaps the copy.
+ * `dst` (ideally page-locked) must stay valid until CLReadImageWait says the read
+ * has landed.  Two reads may be in flight.  CLReadImageWait(n) returns once at most
+ * n reads are still pending (0 = all landed). */
+enum { CLPT_READ_FLOAT4 = 0, CLPT_READ_RGBA8 = 1 };
+void CLReadImageAsync(void *dst, size_t bytes, int format);
+void CLReadImageWait(int leave_pending);
 /* First-hit outputs of sample 0 of the last frame: primitive id (-1 miss),
  * t, (u,v).  Any pointer may be NULL.  Only this rank's rows are valid when
  * sharded. */

@@ -35,12 +35,18 @@ def main(out_path):
             r.set_camera_matrix(cam)
             r.set_params(mode=cl.MODE_NORMAL, depth=2)
             r.create_image(w, h)
-            for _ in range(3):
-                r.execute()
-            ours = min(_frame_ms(r) for _ in range(5))
+            per_engine = {}
+            for engine in (1, 2, 0):  # lane-per-ray, warp-cooperative leaves, automatic
+                cl.lib().CLSetEngine(engine)
+                for _ in range(3):
+                    r.execute()
+                per_engine[engine] = min(_frame_ms(r) for _ in range(5))
+            chosen = int(cl.lib().CLLastEngine())
+            ours = per_engine[0]
             row = {"triangles": len(c) // 3, "tree": label, "rays": w * h, "reference_kernel_opencl_ms": ref_ms,
                    "cuda_ms": ours, "speedup": ref_ms / ours, "reference_Mrays_s": w * h / ref_ms / 1e3,
-                   "cuda_Mrays_s": w * h / ours / 1e3}
+                   "cuda_Mrays_s": w * h / ours / 1e3, "engine_chosen": chosen,
+                   "cuda_ms_engine1_lane_per_ray": per_engine[1], "cuda_ms_engine2_cooperative": per_engine[2]}
             print(row, flush=True)
             out["rows"].append(row)
     r.close()

@@ -433,9 +433,18 @@ def test_full_size_properties_1m(clpt, oracle, renderer):
     from clpathtracer_b200 import scenes
 
     v, c, n = scenes.heightfield(707, False)
-    scene = clpt.build_kd_sah(v, c, n, intersect_cost=1.0, empty_bonus=0.9)  # the bench tree
+    # the tree bench.py renders: exact sweep over every triangle bound (--sah-bins 0), perfect splits
+    scene = clpt.build_kd_sah(v, c, n, nbins=0, intersect_cost=1.0, empty_bonus=0.9)
+    assert scene.stats()["nodes"] > 1_500_000  # (the binned builder makes about half as many)
     w, h = 1920, 1080
     cam = _cam(clpt, "canonical", h)
+    # the bench parameters themselves (depth 5, jitter, several samples) on two bands: one under the
+    # horizon (grazing rays, the costliest rows) and one near the bottom of the frame
+    for band, spp in (((424, 440), 4), ((1000, 1008), 8)):
+        kw = dict(mode=1, depth=5, spp=spp, seed=0, flags=clpt.FLAG_JITTER)
+        img = _render_gpu(renderer, scene, cam, w, h, aov=False, **kw)[0]
+        ref = oracle.render(scene, cam, w, h, rows=band, aov=False, **kw)
+        _assert_bit_equal(img[slice(*band)], ref["rgba"][slice(*band)], f"bench tree, depth 5, {spp} spp, rows {band}")
     img, prim, t, uv = _render_gpu(renderer, scene, cam, w, h, mode=1, depth=2)
     band = (520, 552)
     ref = oracle.render(scene, cam, w, h, mode=1, depth=2, rows=band)
@@ -461,6 +470,122 @@ def test_full_size_properties_1m(clpt, oracle, renderer):
     a_img, a_prim, _, _ = _render_gpu(renderer, scene, cam, w, h, mode=0, depth=2)
     assert np.array_equal(a_prim, prim)
     assert np.array_equal(a_img[prim < 0], np.ones_like(a_img[prim < 0]))
+
+
+def _unorm8(frame):
+    """What write_imagef stores into a CL_UNORM_INT8 image: clamp, x255 in fp32, round to nearest even."""
+    return np.rint(np.clip(frame, 0.0, 1.0).astype(np.float32) * np.float32(255.0)).astype(np.uint8)
+
+
+def test_readback_formats_and_pipeline(clpt, oracle, renderer, scene_cache):
+    """CLReadImageRGBA8 = the float4 frame quantised like the reference's RGBA8 render target
+    (src/GLHandler.c:177-185); CLReadImageAsync delivers the frame that was current when it was
+    called although later frames have been rendered since; progressive frames are normalised."""
+    scene, _ = scene_cache("hf22n")
+    w, h = 333, 197
+    cam = _cam(clpt, "canonical", h)
+    frames = {}
+    for seed in (1, 2, 3):
+        frames[seed] = oracle.render(scene, cam, w, h, mode=1, depth=3, spp=2, seed=seed, flags=clpt.FLAG_JITTER,
+                                     aov=False)["rgba"]
+    img = _render_gpu(renderer, scene, cam, w, h, aov=False, mode=1, depth=3, spp=2, seed=1, flags=clpt.FLAG_JITTER)[0]
+    _assert_bit_equal(img, frames[1], "float4")
+    assert np.array_equal(renderer.read_image_rgba8(), _unorm8(frames[1]))
+    # three reads in flight order: float4 of frame 1, RGBA8 of frame 2, RGBA8 of frame 3
+    a = np.zeros((h, w, 4), dtype=np.float32)
+    b = np.zeros((h, w, 4), dtype=np.uint8)
+    c = np.zeros((h, w, 4), dtype=np.uint8)
+    renderer.read_image_async(a)
+    renderer.set_params(mode=1, depth=3, spp=2, seed=2, flags=clpt.FLAG_JITTER)
+    renderer.execute()
+    renderer.read_image_async(b)
+    renderer.read_wait(1)            # the first read has landed, the second may still be in flight
+    _assert_bit_equal(a, frames[1], "async float4")
+    renderer.set_params(mode=1, depth=3, spp=2, seed=3, flags=clpt.FLAG_JITTER)
+    renderer.execute()
+    renderer.read_image_async(c)     # reuses the first staging buffer
+    renderer.read_wait(0)
+    assert np.array_equal(b, _unorm8(frames[2])) and np.array_equal(c, _unorm8(frames[3]))
+    # progressive: the RGBA8 read-back is the normalised running mean
+    renderer.set_params(mode=1, depth=3, spp=1, seed=4, flags=clpt.FLAG_JITTER | clpt.FLAG_ACCUMULATE)
+    renderer.create_image(w, h)
+    acc = np.zeros((h, w, 4), dtype=np.float32)
+    for base in range(3):
+        renderer.execute()
+        oracle.render(scene, cam, w, h, mode=1, depth=3, spp=1, seed=4, aov=False, sample_base=base,
+                      flags=oracle.FLAG_JITTER | oracle.FLAG_ACCUMULATE, accumulate_into=acc)
+    mean = np.ones_like(acc)
+    mean[..., :3] = acc[..., :3] * (np.float32(1.0) / acc[..., 3:4])
+    _assert_bit_equal(renderer.read_image(), mean, "progressive float4")
+    assert np.array_equal(renderer.read_image_rgba8(), _unorm8(mean))
+    renderer.set_params(mode=0, depth=2)
+
+
+def test_progressive_sharded_accumulates_locally(clpt, oracle, renderer, scene_cache):
+    """Progressive accumulation under row-tile sharding: a rank sums its
+    own rows in its slab, frame after frame, and the rows are placed only on read-back."""
+    scene, _ = scene_cache("hf22n")
+    w, h = 200, 150
+    cam = _cam(clpt, "canonical", h)
+    L = clpt.lib()
+    acc = np.zeros((h, w, 4), dtype=np.float32)
+    kw = dict(mode=1, depth=3, spp=2, seed=6)
+    for base in (0, 2, 4):
+        oracle.render(scene, cam, w, h, aov=False, sample_base=base, accumulate_into=acc,
+                      flags=oracle.FLAG_JITTER | oracle.FLAG_ACCUMULATE, **kw)
+    mean = np.ones_like(acc)
+    mean[..., :3] = acc[..., :3] * (np.float32(1.0) / acc[..., 3:4])
+    try:
+        for rank in range(3):
+            renderer.set_meshes(scene)
+            renderer.set_camera_matrix(cam)
+            renderer.set_params(flags=clpt.FLAG_JITTER | clpt.FLAG_ACCUMULATE, **kw)
+            renderer.create_image(w, h)
+            L.CLSetTileShard(rank, 3, 8)
+            for _ in range(3):
+                renderer.execute()
+            rows = np.array([y for y in range(h) if (y // 8) % 3 == rank], dtype=int)
+            _assert_bit_equal(renderer.read_image()[rows], mean[rows], f"rank {rank}")
+            assert np.array_equal(renderer.read_image_rgba8()[rows], _unorm8(mean)[rows])
+    finally:
+        L.CLSetTileShard(0, 1, 8)
+        renderer.set_params(mode=0, depth=2)
+
+
+def test_band_parity_10m(clpt, oracle, renderer):
+    """BASELINE config 4's scene: 9,999,392 triangles, SAH tree (exact sweep), 3840x2160, one
+    jittered sample, depth 5 -- bit parity with the oracle on a band of rows, and the
+    progressive accumulation of two frames against the oracle's."""
+    from clpathtracer_b200 import scenes
+
+    v, c, n = scenes.heightfield(2236, False)
+    scene = clpt.build_kd_sah(v, c, n, nbins=0, intersect_cost=1.0, empty_bonus=0.9)
+    assert scene.n_tris == 9_999_392
+    w, h = 3840, 2160
+    cam = _cam(clpt, "canonical", h)
+    band = (848, 864)
+    sl = slice(*band)
+    kw = dict(mode=1, depth=5, spp=1, seed=0)
+    img = _render_gpu(renderer, scene, cam, w, h, aov=False, flags=clpt.FLAG_JITTER, **kw)[0]
+    ref = oracle.render(scene, cam, w, h, rows=band, aov=False, flags=oracle.FLAG_JITTER, **kw)
+    _assert_bit_equal(img[sl], ref["rgba"][sl], "10M triangles, 4K, depth 5")
+    assert (img[..., :3] != 1.0).any(axis=-1).mean() > 0.2  # the camera sees the terrain
+    # progressive: two 1-spp frames accumulate to the oracle's two-frame sum, normalised on readback
+    renderer.set_params(flags=clpt.FLAG_JITTER | clpt.FLAG_ACCUMULATE, **kw)
+    renderer.create_image(w, h)
+    renderer.execute()
+    renderer.execute()
+    got = renderer.read_image()
+    acc = np.zeros((h, w, 4), dtype=np.float32)
+    for base in (0, 1):
+        oracle.render(scene, cam, w, h, rows=band, aov=False, flags=oracle.FLAG_JITTER | oracle.FLAG_ACCUMULATE,
+                      sample_base=base, accumulate_into=acc, **kw)
+    want = np.zeros_like(acc[sl])
+    k = np.float32(1.0) / acc[sl][..., 3:4]
+    want[..., :3] = acc[sl][..., :3] * k
+    want[..., 3] = 1.0
+    _assert_bit_equal(got[sl], want, "two accumulated frames")
+    renderer.set_params(mode=0, depth=2)
 
 
 def test_fails_loudly(clpt):

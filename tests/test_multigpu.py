@@ -62,6 +62,23 @@ for tile_rows, engine, direct in ((8, 1, 1), (4, 1, 1), (8, 2, 1), (8, 1, 0)):
         print(f"rank {rank} tile_rows {tile_rows} engine {engine} direct {got_direct} seed {seed}: "
               f"{'ok' if same else 'MISMATCH'}", flush=True)
         ok = ok and same
+    # progressive: every rank accumulates its own rows, nothing crosses GPUs per frame; the
+    # (collective) read-back gathers and normalises.  RGBA8 is the reference's texture format.
+    r.set_params(mode=1, depth=4, spp=2, seed=9, flags=cl.FLAG_JITTER | cl.FLAG_ACCUMULATE)
+    r.create_image(w, h)
+    acc = np.zeros((h, w, 4), dtype=np.float32)
+    for base in (0, 2, 4):
+        r.execute()
+        op.render(scene, cam, w, h, mode=1, depth=4, spp=2, seed=9, aov=False, sample_base=base, accumulate_into=acc,
+                  flags=op.FLAG_JITTER | op.FLAG_ACCUMULATE)
+    mean = np.ones_like(acc)
+    mean[..., :3] = acc[..., :3] * (np.float32(1.0) / acc[..., 3:4])
+    q = np.rint(np.clip(mean, 0.0, 1.0).astype(np.float32) * np.float32(255.0)).astype(np.uint8)
+    same = np.array_equal(r.read_image().view(np.uint32), mean.view(np.uint32)) and \
+        np.array_equal(r.read_image_rgba8(), q)
+    print(f"rank {rank} tile_rows {tile_rows} engine {engine} direct {got_direct} progressive: "
+          f"{'ok' if same else 'MISMATCH'}", flush=True)
+    ok = ok and same
     L.CLDistShutdown()
 os.environ.pop("CLPT_P2P", None)
 r.close()
@@ -84,5 +101,5 @@ def test_two_rank_frame_assembly(tmp_path):
            "127.0.0.1", "--master-port", "29541", str(script)]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
-    assert p.stdout.count(": ok") == 16, p.stdout
+    assert p.stdout.count(": ok") == 24, p.stdout
     print(p.stderr[-1500:])  # shown with -s: mapping diagnostics
