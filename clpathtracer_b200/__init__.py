@@ -109,6 +109,9 @@ def lib() -> C.CDLL:
         "CLSetObjects": (None, [vp, sz]), "CLSetMeshes": (None, [vp]),
         "CLSetMeshesRaw": (None, [vp, sz, vp, sz, vp, sz, vp, sz, vp, sz]),
         "CLSetMaterials": (None, [vp, sz, vp, sz]),
+        "CLBuildMeshes": (None, [vp, sz, vp, sz, vp, sz]), "CLSetBuildParams": (None, [i, i, f, f, f]),
+        "CLLastBuildMs": (None, [C.POINTER(f), C.POINTER(f)]), "CLBuildStats": (None, [C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
+        "CLDownloadKd": (None, [C.POINTER(KD)]), "CLDebugReadPacked": (sz, [i, vp, sz]),
         "CLDeleteImage": (None, []), "CLCreateImage": (None, [u]), "CLExecute": (None, [i, i]),
         "CLSelectDevice": (None, [i]), "CLSetRenderParams": (None, [i, i, i, u, i]),
         "CLSetMaxLeafVisits": (None, [i]), "CLSetEngine": (None, [i]), "CLLastEngine": (i, []), "CLCreateImageHeadless": (None, [i, i]),
@@ -302,6 +305,32 @@ class Renderer:
         C.memmove(models, C.byref(k), C.sizeof(KD))
         self.L.CLSetMeshes(models)
         self.L.delete_list(models)  # the caller frees only the outer list (src/game.c:177-178)
+
+    def build_meshes(self, verts: np.ndarray, corners: np.ndarray, norms: np.ndarray | None = None) -> None:
+        """Upload a mesh and build its kd-tree on the device (CLBuildMeshes)."""
+        v4 = _as_vec4(verts)
+        c4 = np.ascontiguousarray(corners, dtype=np.int32).reshape(-1, 4)
+        n4 = _as_vec4(norms) if norms is not None and len(norms) else None
+        self.L.CLBuildMeshes(v4.ctypes.data, v4.nbytes, c4.ctypes.data, c4.nbytes,
+                             None if n4 is None else n4.ctypes.data, 0 if n4 is None else n4.nbytes)
+
+    def download_kd(self) -> "Scene":
+        """The device-built tree as a Scene (wire format) for the oracle."""
+        k = KD()
+        self.L.CLDownloadKd(C.byref(k))
+        return Scene.from_kd(k)
+
+    def build_ms(self) -> tuple[float, float]:
+        b, p = C.c_float(0), C.c_float(0)
+        self.L.CLLastBuildMs(C.byref(b), C.byref(p))
+        return b.value, p.value
+
+    def read_packed(self, which: int) -> np.ndarray:
+        n = self.L.CLDebugReadPacked(which, None, 0)
+        out = np.zeros(n, dtype=np.uint8)
+        if n:
+            self.L.CLDebugReadPacked(which, out.ctypes.data, n)
+        return out
 
     def set_materials(self, materials: np.ndarray, tri_material: np.ndarray | None = None) -> None:
         m = np.ascontiguousarray(materials, dtype=np.float32).reshape(-1, 8)

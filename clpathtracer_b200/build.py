@@ -22,7 +22,7 @@ LIB = PKG / "libclpt.so"
 
 HOST_C = ["host/hostlist.c", "host/vecmath.c", "host/kd_build.c", "host/model_io.c", "host/frame_sched.c"]
 HOST_CXX = ["cuda/scene_pack.cpp"]
-CUDA = ["cuda/render_kernel.cu", "cuda/gl_interop.cu", "cuda/clstate.cu",
+CUDA = ["cuda/render_kernel.cu", "cuda/kd_build_gpu.cu", "cuda/gl_interop.cu", "cuda/clstate.cu",
         "cuda/clhandler.cu"]
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -67,6 +67,7 @@ struct ClptFrame {
     int width, height;
     int mode, depth, spp, flags;
     int log2_sample_lanes;       // lanes per pixel = 1 << this (largest power of two <= min(spp, 32))
+    int log2_warps_per_pixel;    // warps of a block sharing one pixel's samples (> 0 only at >= 64 spp)
     unsigned int seed, sample_base;
     int max_leaf_visits;
     int rank, nranks, tile_rows; // row-tile sharding; nranks == 1 -> whole image

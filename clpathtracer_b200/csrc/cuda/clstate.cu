@@ -21,6 +21,7 @@
 #include "clpt_device.cuh"
 #include "clpt_host.h"
 #include "../host/frame_sched.h"
+#include "kd_build_gpu.h"
 #include "scene_pack.h"
 
 #define CU(call) handle_err((int)(call), __FILE__, __LINE__)
@@ -125,6 +126,7 @@ struct {
     cudaDeviceProp prop;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     cudaEvent_t ev_user[8] = {};
+    cudaEvent_t ev_build[3] = {};
 
     kd host_kd = { nullptr, nullptr, nullptr, nullptr, nullptr };
     bool owns_kd = false;
@@ -133,6 +135,14 @@ struct {
     DevBuf<float4> leaves, tri, norms;
     DevBuf<int4> corners;
     DevBuf<int> lut;
+    // device-side build (CLBuildMeshes): the mesh, the wire-format tree and its re-layout all live
+    // on the device; `scene` then points into gpu_packed instead of the buffers above
+    DevBuf<float4> verts;
+    ClptGpuBuildParams build_params;
+    ClptGpuTree gpu_tree;
+    ClptGpuPacked gpu_packed;
+    bool scene_on_gpu = false;
+    float last_build_ms = 0, last_pack_ms = 0;
     DevBuf<unsigned char> objects;
     int objcount = 0;
     DevBuf<ClptMaterial> materials;
@@ -220,11 +230,11 @@ int local_rows_for(int height) {
 
 void rebuild_scene_struct() {
     ClptScene &S = St.scene;
-    S.nodes = St.nodes.ptr;
-    S.leaves = St.leaves.ptr;
-    S.tri = St.tri.ptr;
+    S.nodes = St.scene_on_gpu ? St.gpu_packed.nodes : St.nodes.ptr;
+    S.leaves = St.scene_on_gpu ? St.gpu_packed.leaves : St.leaves.ptr;
+    S.tri = St.scene_on_gpu ? St.gpu_packed.tri : St.tri.ptr;
     S.corners = St.corners.ptr;
-    S.lut = St.lut.ptr;
+    S.lut = St.scene_on_gpu ? St.gpu_packed.lut : St.lut.ptr;
     S.norms = St.norms.ptr;
     S.tri_material = St.tri_material.ptr;
     S.materials = St.materials.ptr;
@@ -261,6 +271,7 @@ void upload_scene(const kdnode *nodes, size_t node_bytes, const int *tri_indices
     }
     // per-triangle materials belong to the previous mesh
     St.tri_material.release();
+    St.scene_on_gpu = false;
     ClptScene &S = St.scene;
     S.n_nodes = packed.n_nodes;
     S.n_leaves = packed.n_leaves;
@@ -618,6 +629,15 @@ void clpt_state_launch_frame(int width, int height) {
     F.flags = St.flags;
     F.log2_sample_lanes = 0;
     while (F.log2_sample_lanes < 5 && (2 << F.log2_sample_lanes) <= St.spp) F.log2_sample_lanes++;
+    // at >= 64 spp the samples of a pixel are spread over 2, 4 or 8 warps (render_kernel.cu)
+    F.log2_warps_per_pixel = 0;
+    while (F.log2_warps_per_pixel < 3 && (64 << F.log2_warps_per_pixel) <= St.spp) F.log2_warps_per_pixel++;
+    if (const char *e = getenv("CLPT_WARPS_PER_PIXEL")) {
+        const int want = atoi(e);
+        int lg = 0;
+        while ((2 << lg) <= want && lg < 3) lg++;
+        if (F.log2_sample_lanes == 5 || lg == 0) F.log2_warps_per_pixel = lg;
+    }
     F.seed = St.seed;
     F.sample_base = St.sample_base;
     F.max_leaf_visits = St.max_leaf_visits;
@@ -760,6 +780,7 @@ void CLInit(const char *kernel_filename, const char *kernel_name) {
     CU(cudaEventCreate(&St.ev_start));
     CU(cudaEventCreate(&St.ev_stop));
     for (auto &e : St.ev_user) CU(cudaEventCreate(&e));
+    for (auto &e : St.ev_build) CU(cudaEventCreate(&e));
     memset(St.cam, 0, sizeof(St.cam));
     clpt_pack_alloc = pinned_alloc; // the packed scene is staged in page-locked memory
     clpt_pack_free = pinned_free;
@@ -786,6 +807,19 @@ void CLTerminate(void) {
     St.norms.release();
     St.corners.release();
     St.lut.release();
+    St.verts.release();
+    {
+        auto drop = [](auto *&p) {
+            if (p) CU(cudaFree(p));
+            p = nullptr;
+        };
+        drop(St.gpu_tree.wire), drop(St.gpu_tree.tri_indices);
+        drop(St.gpu_packed.nodes), drop(St.gpu_packed.leaves), drop(St.gpu_packed.tri), drop(St.gpu_packed.lut);
+        St.gpu_tree = ClptGpuTree();
+        St.gpu_packed = ClptGpuPacked();
+        St.scene_on_gpu = false;
+        clpt_gpu_build_release();
+    }
     St.objects.release();
     St.materials.release();
     St.tri_material.release();
@@ -814,6 +848,7 @@ void CLTerminate(void) {
     CU(cudaEventDestroy(St.ev_start));
     CU(cudaEventDestroy(St.ev_stop));
     for (auto &e : St.ev_user) CU(cudaEventDestroy(e));
+    for (auto &e : St.ev_build) CU(cudaEventDestroy(e));
     CU(cudaStreamDestroy(St.stream));
     St.stream = nullptr;
     St.have_scene = St.have_image = St.headless = false;
@@ -878,6 +913,117 @@ void CLSetMeshesRaw(const void *nodes, size_t node_bytes, const int *tri_indices
     release_host_kd();
     upload_scene((const kdnode *)nodes, node_bytes, tri_indices, tri_index_bytes, (const cl_int3 *)tris,
                  tri_bytes, (const Vector4 *)verts, vert_bytes, (const Vector4 *)norms, norm_bytes);
+}
+
+void CLSetBuildParams(int max_depth, int min_split, float traversal_cost, float intersect_cost, float empty_bonus) {
+    St.build_params.max_depth = max_depth;
+    St.build_params.min_split = min_split < 2 ? 2 : min_split;
+    St.build_params.ct = traversal_cost;
+    St.build_params.ci = intersect_cost;
+    St.build_params.empty_bonus = empty_bonus;
+}
+
+void CLBuildMeshes(const void *verts, size_t vert_bytes, const void *tris, size_t tri_bytes, const void *norms,
+                   size_t norm_bytes) {
+    require_init("CLBuildMeshes");
+    release_host_kd();
+    const size_t n_verts = vert_bytes / sizeof(Vector4), n_corners = tri_bytes / sizeof(cl_int3);
+    const size_t n_norms = norms ? norm_bytes / sizeof(Vector4) : 0;
+    if (n_verts == 0 || n_corners < 3) FATAL("CLBuildMeshes: empty mesh");
+    // the mesh crosses PCIe once; everything after it happens on the device
+    St.verts.resize(n_verts);
+    CU(cudaMemcpyAsync(St.verts.ptr, verts, n_verts * sizeof(float4), cudaMemcpyHostToDevice, St.stream));
+    St.corners.resize(n_corners);
+    CU(cudaMemcpyAsync(St.corners.ptr, tris, n_corners * sizeof(int4), cudaMemcpyHostToDevice, St.stream));
+    if (n_norms) {
+        St.norms.resize(n_norms);
+        CU(cudaMemcpyAsync(St.norms.ptr, norms, n_norms * sizeof(float4), cudaMemcpyHostToDevice, St.stream));
+    } else {
+        St.norms.release();
+    }
+    St.tri_material.release();
+    char err[256] = "";
+    CU(cudaEventRecord(St.ev_build[0], St.stream));
+    if (!clpt_gpu_build(St.verts.ptr, (int)n_verts, St.corners.ptr, (int)(n_corners / 3), St.build_params, St.gpu_tree,
+                        St.stream, err, sizeof err)) {
+        fprintf(stderr, "CLBuildMeshes: invalid scene: %s\n", err);
+        exit(EXIT_FAILURE);
+    }
+    CU(cudaEventRecord(St.ev_build[1], St.stream));
+    if (!clpt_gpu_pack(St.gpu_tree, St.verts.ptr, St.corners.ptr, (int)(n_corners / 3), St.gpu_packed, St.stream, err,
+                       sizeof err)) {
+        fprintf(stderr, "CLBuildMeshes: invalid scene: %s\n", err);
+        exit(EXIT_FAILURE);
+    }
+    CU(cudaEventRecord(St.ev_build[2], St.stream));
+    CU(cudaStreamSynchronize(St.stream));
+    CU(cudaEventElapsedTime(&St.last_build_ms, St.ev_build[0], St.ev_build[1]));
+    CU(cudaEventElapsedTime(&St.last_pack_ms, St.ev_build[1], St.ev_build[2]));
+    St.scene_on_gpu = true;
+    ClptScene &S = St.scene;
+    S.n_nodes = St.gpu_packed.n_nodes;
+    S.n_leaves = St.gpu_packed.n_leaves;
+    S.n_refs = St.gpu_packed.n_refs;
+    S.n_prims = (int)(n_corners / 3);
+    for (int a = 0; a < 3; a++) {
+        S.root_min[a] = St.gpu_packed.root_min[a];
+        S.root_max[a] = St.gpu_packed.root_max[a];
+        S.lut_dim[a] = St.gpu_packed.lut_dim[a];
+        S.lut_scale[a] = St.gpu_packed.lut_scale[a];
+    }
+    rebuild_scene_struct();
+    St.have_scene = true;
+    St.auto_engine = (St.gpu_packed.n_refs > 0 && St.gpu_packed.fat_refs * 2 > (size_t)St.gpu_packed.n_refs) ? 2 : 1;
+    if (const char *e = getenv("CLPT_ENGINE")) {
+        if (atoi(e) == 1 || atoi(e) == 2) St.auto_engine = atoi(e);
+    }
+}
+
+void CLLastBuildMs(float *build_ms, float *pack_ms) {
+    if (build_ms) *build_ms = St.last_build_ms;
+    if (pack_ms) *pack_ms = St.last_pack_ms;
+}
+
+void CLBuildStats(int *nodes, int *tri_refs, int *levels) {
+    if (nodes) *nodes = St.gpu_tree.n_nodes;
+    if (tri_refs) *tri_refs = St.gpu_tree.n_refs;
+    if (levels) *levels = St.gpu_tree.levels;
+}
+
+void CLDownloadKd(kd *out) {
+    require_init("CLDownloadKd");
+    if (!St.scene_on_gpu) FATAL("CLDownloadKd: the current scene was not built by CLBuildMeshes");
+    CU(cudaStreamSynchronize(St.stream));
+    const size_t n = (size_t)St.gpu_tree.n_nodes, r = (size_t)St.gpu_tree.n_refs;
+    out->node_vec = (kdnode *)init_list(n, sizeof(kdnode));
+    out->tri_indices = (int *)init_list(r, sizeof(int));
+    out->vert_vec = (Vector4 *)init_list(St.verts.count, sizeof(Vector4));
+    out->tri_vec = (cl_int3 *)init_list(St.corners.count, sizeof(cl_int3));
+    out->norm_vec = (Vector4 *)init_list(St.norms.count, sizeof(Vector4));
+    CU(cudaMemcpy(out->node_vec, St.gpu_tree.wire, n * sizeof(kdnode), cudaMemcpyDeviceToHost));
+    if (r) CU(cudaMemcpy(out->tri_indices, St.gpu_tree.tri_indices, r * sizeof(int), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out->vert_vec, St.verts.ptr, St.verts.count * sizeof(Vector4), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out->tri_vec, St.corners.ptr, St.corners.count * sizeof(cl_int3), cudaMemcpyDeviceToHost));
+    if (St.norms.count) {
+        CU(cudaMemcpy(out->norm_vec, St.norms.ptr, St.norms.count * sizeof(Vector4), cudaMemcpyDeviceToHost));
+    }
+}
+
+size_t CLDebugReadPacked(int which, void *dst, size_t bytes) {
+    require_init("CLDebugReadPacked");
+    if (!St.have_scene) FATAL("CLDebugReadPacked: no scene");
+    const ClptScene &S = St.scene;
+    const void *src = nullptr;
+    size_t have = 0;
+    switch (which) {
+    case 0: src = S.nodes, have = (size_t)S.n_nodes * sizeof(uint2); break;
+    case 1: src = S.leaves, have = (size_t)S.n_leaves * 4 * sizeof(float4); break;
+    case 2: src = S.tri, have = (size_t)S.n_refs * 3 * sizeof(float4); break;
+    case 3: src = S.lut, have = (size_t)S.lut_dim[0] * S.lut_dim[1] * S.lut_dim[2] * sizeof(int); break;
+    default: FATAL("CLDebugReadPacked: which must be 0 (nodes), 1 (leaves), 2 (triangles) or 3 (start table)");
+    }
+    if (dst && bytes >= have && have) CU(cudaMemcpy(dst, src, have, cudaMemcpyDeviceToHost));
+    return have;
 }
 
 void CLSetMaterials(const CLMaterial *materials, size_t material_bytes, const int *tri_material,

@@ -1,0 +1,848 @@
+// kd_build_gpu.cu -- kd-tree construction on the device.
+//
+// The reference builds its tree on one host core (src/kd_tree.c:95-200, ~20 s for a
+// million triangles) and this library's host builders (csrc/host/kd_build.c) on all of
+// them (~1 s).  For scenes that change every frame (BASELINE config 5) even that is the
+// frame: this file builds the tree where the triangles already are.
+//
+// Level-synchronous binned SAH, one pass over the references per level:
+//   bin      every reference adds its bounds to its node's 3 x 2 x 32 histograms
+//            (where a bound starts, where it ends; shared-memory copy for the node a
+//            block starts in, so the few huge nodes of the top levels do not serialise)
+//   choose   one warp per node: prefix sums over the bins, the surface-area heuristic
+//            cost(plane) = Ct + Ci (SA(L) NL + SA(R) NR) / SA(cell), x empty_bonus when a
+//            side is empty (the same cost as build_kd_sah, kd_build.c), leaf when no plane
+//            beats Ci N
+//   scan     three running counts over the references (goes left, goes right, stays in a
+//            finished leaf) -- the references of a node are contiguous and keep their
+//            order, so the counts place every reference of the next level without
+//            atomics: the tree and the order of the triangles inside each leaf (which
+//            decides ties, src/kernel.cl:344) are DETERMINISTIC, and every GPU of a node
+//            builds the same bytes from the same mesh
+//   emit     split and leaf records in the reference's 68-byte wire format
+//            (include/kd_tree.h:31-50), children two by two, ropes inherited from the
+//            parent (src/kd_tree.c:64-83)
+// and after the last level one thread per leaf face pushes its rope down to the deepest
+// node that still covers the face (kd_build.c: push_down_link, full).
+//
+// The output is the wire format ON THE DEVICE; scene_pack_gpu.cu turns it into the
+// traversal layout without leaving the device, and CLDownloadKd hands it to a host that
+// wants to look at it (the parity tests walk it with the oracle).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "CLHandler.h"
+#include "clpt_device.cuh"
+#include "kd_build_gpu.h"
+
+#define CU(call) handle_err((int)(call), __FILE__, __LINE__)
+
+namespace {
+
+constexpr int NBINS = 32;
+constexpr int SCAN_BLOCK = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
+
+// A node of the level being split.
+struct ANode {
+    float mn[3], mx[3];
+    int begin, count; // its references: [begin, begin + count) of the level's reference array
+    int out;          // index of its record in the wire array
+    int links[6];     // neighbour across each face (wire node index, -1 = outside), not yet pushed down
+    int depth_left;
+};
+
+struct Decision { // what `choose` decided for a node
+    float plane;
+    int axis;      // -1: the node becomes a leaf
+    int rank;      // exclusive rank among this level's splits (filled by the scan over nodes)
+};
+
+struct Triple {
+    unsigned l, r, f;
+};
+__host__ __device__ inline Triple operator+(Triple a, Triple b) { return Triple{ a.l + b.l, a.r + b.r, a.f + b.f }; }
+
+// ---- bounds of every triangle (SoA) ---------------------------------------------------
+__global__ void tri_bounds_kernel(const float4 *__restrict__ verts, const int4 *__restrict__ corners, int n_tris,
+                                  int n_verts, float *__restrict__ lo, float *__restrict__ hi, int *__restrict__ bad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_tris) return;
+    const int a = corners[3 * (size_t)i].x, b = corners[3 * (size_t)i + 1].x, c = corners[3 * (size_t)i + 2].x;
+    if (a < 0 || b < 0 || c < 0 || a >= n_verts || b >= n_verts || c >= n_verts) {
+        atomicExch(bad, 1);
+        return;
+    }
+    const float4 A = verts[a], B = verts[b], C = verts[c];
+    lo[i] = fminf(fminf(A.x, B.x), C.x);
+    hi[i] = fmaxf(fmaxf(A.x, B.x), C.x);
+    lo[n_tris + i] = fminf(fminf(A.y, B.y), C.y);
+    hi[n_tris + i] = fmaxf(fmaxf(A.y, B.y), C.y);
+    lo[2 * (size_t)n_tris + i] = fminf(fminf(A.z, B.z), C.z);
+    hi[2 * (size_t)n_tris + i] = fmaxf(fmaxf(A.z, B.z), C.z);
+}
+
+// Scene box: min/max over the triangle bounds.  Floats compare like their sign-adjusted
+// integer images, so the reduction is integer atomics (exact, order-independent).
+__device__ __forceinline__ int float_key(float f) {
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
+__global__ void scene_box_kernel(const float *__restrict__ lo, const float *__restrict__ hi, int n_tris,
+                                 int *__restrict__ box_keys /* [6]: min xyz, max xyz */) {
+    int mn[3] = { INT_MAX, INT_MAX, INT_MAX }, mx[3] = { INT_MIN, INT_MIN, INT_MIN };
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_tris; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            mn[a] = min(mn[a], float_key(lo[(size_t)a * n_tris + i]));
+            mx[a] = max(mx[a], float_key(hi[(size_t)a * n_tris + i]));
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        for (int off = 16; off > 0; off >>= 1) {
+            mn[a] = min(mn[a], __shfl_down_sync(0xffffffffu, mn[a], off));
+            mx[a] = max(mx[a], __shfl_down_sync(0xffffffffu, mx[a], off));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(box_keys + a, mn[a]);
+            atomicMax(box_keys + 3 + a, mx[a]);
+        }
+    }
+}
+
+__global__ void root_kernel(const int *__restrict__ box_keys, int n_tris, int max_depth, ANode *__restrict__ nodes,
+                            int *__restrict__ ref_tri, int *__restrict__ ref_node) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        ANode r;
+        for (int a = 0; a < 3; a++) {
+            r.mn[a] = key_float(box_keys[a]);
+            r.mx[a] = key_float(box_keys[3 + a]);
+        }
+        r.begin = 0;
+        r.count = n_tris;
+        r.out = 0;
+        for (int f = 0; f < 6; f++) r.links[f] = -1;
+        r.depth_left = max_depth;
+        nodes[0] = r;
+    }
+    if (i < n_tris) {
+        ref_tri[i] = i;
+        ref_node[i] = 0;
+    }
+}
+
+// ---- bin -------------------------------------------------------------------------------
+__device__ __forceinline__ int bin_of(float x, float mn, float scale) {
+    const int b = __float2int_rd((x - mn) * scale); // NaN -> 0, saturates
+    return min(max(b, 0), NBINS - 1);
+}
+
+__global__ void __launch_bounds__(256)
+bin_kernel(const ANode *__restrict__ nodes, const int *__restrict__ ref_tri, const int *__restrict__ ref_node,
+           int n_refs, const float *__restrict__ lo, const float *__restrict__ hi, int n_tris, int min_split,
+           unsigned *__restrict__ hist /* [node][axis][start|end][bin] */) {
+    __shared__ unsigned local[3 * 2 * NBINS];
+    __shared__ int home; // the node this block's first reference belongs to
+    const int first = blockIdx.x * blockDim.x;
+    if (threadIdx.x == 0) home = ref_node[min(first, n_refs - 1)];
+    for (int k = threadIdx.x; k < 3 * 2 * NBINS; k += blockDim.x) local[k] = 0;
+    __syncthreads();
+    const int i = first + threadIdx.x;
+    if (i < n_refs) {
+        const int a = ref_node[i];
+        const ANode &nd = nodes[a];
+        if (nd.count >= min_split && nd.depth_left > 0) {
+            const int t = ref_tri[i];
+            unsigned *dst = a == home ? local : hist + (size_t)a * (3 * 2 * NBINS);
+#pragma unroll
+            for (int ax = 0; ax < 3; ax++) {
+                const float ext = nd.mx[ax] - nd.mn[ax];
+                const float scale = ext > 0.0f ? (float)NBINS / ext : 0.0f;
+                const int bs = bin_of(lo[(size_t)ax * n_tris + t], nd.mn[ax], scale);
+                const int be = bin_of(hi[(size_t)ax * n_tris + t], nd.mn[ax], scale);
+                atomicAdd(dst + (ax * 2 + 0) * NBINS + bs, 1u);
+                atomicAdd(dst + (ax * 2 + 1) * NBINS + be, 1u);
+            }
+        }
+    }
+    __syncthreads();
+    unsigned *dst = hist + (size_t)home * (3 * 2 * NBINS);
+    for (int k = threadIdx.x; k < 3 * 2 * NBINS; k += blockDim.x) {
+        if (local[k]) atomicAdd(dst + k, local[k]);
+    }
+}
+
+// ---- choose ----------------------------------------------------------------------------
+__device__ __forceinline__ float box_area(float ex, float ey, float ez) { return 2.0f * (ex * ey + ey * ez + ez * ex); }
+
+__global__ void __launch_bounds__(256)
+choose_kernel(const ANode *__restrict__ nodes, int n_nodes, const unsigned *__restrict__ hist, int min_split, float ct,
+              float ci, float empty_bonus, Decision *__restrict__ decisions) {
+    const int lane = threadIdx.x & 31;
+    const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (a >= n_nodes) return;
+    const ANode nd = nodes[a];
+    Decision d;
+    d.axis = -1;
+    d.plane = 0.0f;
+    d.rank = 0;
+    if (nd.count >= min_split && nd.depth_left > 0) {
+        const float ext[3] = { nd.mx[0] - nd.mn[0], nd.mx[1] - nd.mn[1], nd.mx[2] - nd.mn[2] };
+        const float area = box_area(ext[0], ext[1], ext[2]);
+        const float inv_area = area > 0.0f ? 1.0f / area : 0.0f;
+        float best = ci * (float)nd.count; // the cost of leaving the node a leaf
+        int best_code = -1;                // axis * NBINS + plane index
+        const unsigned *h = hist + (size_t)a * (3 * 2 * NBINS);
+        for (int ax = 0; ax < 3; ax++) {
+            if (!(ext[ax] > 0.0f) || !(inv_area > 0.0f)) continue;
+            unsigned s = h[(ax * 2 + 0) * NBINS + lane], e = h[(ax * 2 + 1) * NBINS + lane];
+            // exclusive prefix sums: plane k (k = lane, 1..31) sits at the low edge of bin k
+            unsigned ps = s, pe = e;
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned us = __shfl_up_sync(0xffffffffu, ps, off), ue = __shfl_up_sync(0xffffffffu, pe, off);
+                if (lane >= off) {
+                    ps += us;
+                    pe += ue;
+                }
+            }
+            const int nl = (int)(ps - s), nr = nd.count - (int)(pe - e);
+            float cost = 3.0e38f;
+            if (lane >= 1) {
+                float el[3] = { ext[0], ext[1], ext[2] }, er[3] = { ext[0], ext[1], ext[2] };
+                el[ax] = ext[ax] * ((float)lane / (float)NBINS);
+                er[ax] = ext[ax] - el[ax];
+                cost = ct + ci * (box_area(el[0], el[1], el[2]) * (float)nl + box_area(er[0], er[1], er[2]) * (float)nr) *
+                                inv_area;
+                if (nl == 0 || nr == 0) cost *= empty_bonus;
+                // a plane that leaves everything on both sides separates nothing
+                if (nl == nd.count && nr == nd.count) cost = 3.0e38f;
+            }
+            // warp argmin, lowest (axis, plane) first among equals
+            float c = cost;
+            int code = ax * NBINS + lane;
+            for (int off = 16; off > 0; off >>= 1) {
+                const float oc = __shfl_xor_sync(0xffffffffu, c, off);
+                const int ocode = __shfl_xor_sync(0xffffffffu, code, off);
+                if (oc < c || (oc == c && ocode < code)) {
+                    c = oc;
+                    code = ocode;
+                }
+            }
+            if (c < best) {
+                best = c;
+                best_code = code;
+            }
+        }
+        if (best_code >= 0) {
+            const int ax = best_code / NBINS, k = best_code % NBINS;
+            float plane = nd.mn[ax] + ext[ax] * ((float)k / (float)NBINS);
+            // keep the plane strictly inside the cell so that both children are thinner than it
+            if (plane > nd.mn[ax] && plane < nd.mx[ax]) {
+                d.axis = ax;
+                d.plane = plane;
+            }
+        }
+    }
+    if (lane == 0) decisions[a] = d;
+}
+
+// ---- scans -----------------------------------------------------------------------------
+// Where a reference goes.  Left: its bound starts below the plane (or it lies in the
+// plane); right: it ends above the plane.  Triangles that only touch the plane from one
+// side stay on that side (kd_build.c, partition).
+__device__ __forceinline__ Triple ref_flags(const ANode *__restrict__ nodes, const Decision *__restrict__ dec,
+                                            const int *__restrict__ ref_tri, const int *__restrict__ ref_node,
+                                            const float *__restrict__ lo, const float *__restrict__ hi, int n_tris,
+                                            int i) {
+    const int a = ref_node[i];
+    const Decision d = dec[a];
+    if (d.axis < 0) return Triple{ 0u, 0u, 1u };
+    const int t = ref_tri[i];
+    const float l = lo[(size_t)d.axis * n_tris + t], h = hi[(size_t)d.axis * n_tris + t];
+    const bool right = h > d.plane;
+    const bool left = l < d.plane || !right; // (lying in the plane, or wholly below it)
+    return Triple{ left ? 1u : 0u, right ? 1u : 0u, 0u };
+}
+
+template <typename F>
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_tile_sums_kernel(int n, F f, Triple *__restrict__ tile_sums) {
+    __shared__ Triple warp_sums[SCAN_BLOCK / 32];
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    Triple s = { 0u, 0u, 0u };
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        if (base + k < n) s = s + f(base + k);
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        s.l += __shfl_down_sync(0xffffffffu, s.l, off);
+        s.r += __shfl_down_sync(0xffffffffu, s.r, off);
+        s.f += __shfl_down_sync(0xffffffffu, s.f, off);
+    }
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Triple t = { 0u, 0u, 0u };
+        for (int w = 0; w < SCAN_BLOCK / 32; w++) t = t + warp_sums[w];
+        tile_sums[blockIdx.x] = t;
+    }
+}
+
+// Exclusive scan of the tile sums in place, one block; the grand total lands in total[0].
+__global__ void __launch_bounds__(1024) scan_tile_offsets_kernel(Triple *__restrict__ tile_sums, int n_tiles,
+                                                                 Triple *__restrict__ total) {
+    __shared__ Triple warp_sums[32];
+    __shared__ Triple carry;
+    if (threadIdx.x == 0) carry = Triple{ 0u, 0u, 0u };
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024) {
+        const int i = base + threadIdx.x;
+        const Triple v = i < n_tiles ? tile_sums[i] : Triple{ 0u, 0u, 0u };
+        Triple s = v;
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned l = __shfl_up_sync(0xffffffffu, s.l, off), r = __shfl_up_sync(0xffffffffu, s.r, off),
+                           f = __shfl_up_sync(0xffffffffu, s.f, off);
+            if ((threadIdx.x & 31) >= off) s = s + Triple{ l, r, f };
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = s;
+        __syncthreads();
+        Triple before = carry;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) before = before + warp_sums[w];
+        if (i < n_tiles) tile_sums[i] = Triple{ before.l + s.l - v.l, before.r + s.r - v.r, before.f + s.f - v.f };
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = Triple{ before.l + s.l, before.r + s.r, before.f + s.f };
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) total[0] = carry;
+}
+
+// Exclusive scan values for every item (plus one past the end = totals).
+template <typename F>
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_write_kernel(int n, F f, const Triple *__restrict__ tile_offsets,
+                                                                const Triple *__restrict__ total,
+                                                                Triple *__restrict__ out /* n + 1 */) {
+    __shared__ Triple warp_sums[SCAN_BLOCK / 32];
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    Triple v[SCAN_ITEMS];
+    Triple s = { 0u, 0u, 0u };
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        v[k] = base + k < n ? f(base + k) : Triple{ 0u, 0u, 0u };
+        s = s + v[k];
+    }
+    Triple inc = s;
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned l = __shfl_up_sync(0xffffffffu, inc.l, off), r = __shfl_up_sync(0xffffffffu, inc.r, off),
+                       ff = __shfl_up_sync(0xffffffffu, inc.f, off);
+        if ((threadIdx.x & 31) >= off) inc = inc + Triple{ l, r, ff };
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    Triple before = tile_offsets[blockIdx.x];
+    for (int w = 0; w < (int)(threadIdx.x >> 5); w++) before = before + warp_sums[w];
+    Triple run = Triple{ before.l + inc.l - s.l, before.r + inc.r - s.r, before.f + inc.f - s.f };
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        if (base + k < n) out[base + k] = run;
+        run = run + v[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = total[0];
+}
+
+struct RefFlagFn {
+    const ANode *nodes;
+    const Decision *dec;
+    const int *ref_tri, *ref_node;
+    const float *lo, *hi;
+    int n_tris;
+    __device__ Triple operator()(int i) const { return ref_flags(nodes, dec, ref_tri, ref_node, lo, hi, n_tris, i); }
+};
+struct SplitFlagFn { // over the nodes of a level: .l counts splits, .f counts leaves
+    const Decision *dec;
+    __device__ Triple operator()(int i) const { return dec[i].axis >= 0 ? Triple{ 1u, 0u, 0u } : Triple{ 0u, 0u, 1u }; }
+};
+
+// ---- emit ------------------------------------------------------------------------------
+// Wire record of node `out`: 17 words (include/kd_tree.h:31-50; the struct is packed, so it
+// is written word by word).
+__device__ __forceinline__ void write_box(int *__restrict__ wire, int out, const float *mn, const float *mx) {
+    int *w = wire + 17 * (size_t)out;
+    w[0] = __float_as_int(mn[0]);
+    w[1] = __float_as_int(mn[1]);
+    w[2] = __float_as_int(mn[2]);
+    w[3] = 0;
+    w[4] = __float_as_int(mx[0]);
+    w[5] = __float_as_int(mx[1]);
+    w[6] = __float_as_int(mx[2]);
+    w[7] = 0;
+}
+
+__global__ void emit_kernel(const ANode *__restrict__ nodes, int n_nodes, const Decision *__restrict__ dec,
+                            const Triple *__restrict__ node_scan /* n_nodes + 1 */,
+                            const Triple *__restrict__ ref_scan /* n_refs + 1 */, int next_out_base, int leaf_ref_base,
+                            int *__restrict__ wire, ANode *__restrict__ next_nodes) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n_nodes) return;
+    const ANode nd = nodes[a];
+    const Decision d = dec[a];
+    write_box(wire, nd.out, nd.mn, nd.mx);
+    int *w = wire + 17 * (size_t)nd.out;
+    if (d.axis < 0) {
+        w[8] = 1; // KD_LEAF
+        w[9] = nd.count > 0 ? leaf_ref_base + (int)ref_scan[nd.begin].f : -1;
+        w[10] = nd.count;
+        for (int f = 0; f < 6; f++) w[11 + f] = nd.links[f];
+        return;
+    }
+    const int rank = (int)node_scan[a].l;
+    const int lo_out = next_out_base + 2 * rank, hi_out = lo_out + 1;
+    w[8] = 0; // KD_SPLIT
+    w[9] = __float_as_int(d.plane);
+    w[10] = d.axis;
+    w[11] = lo_out;
+    w[12] = hi_out;
+    w[13] = w[14] = w[15] = w[16] = 0;
+    const Triple at_begin = ref_scan[nd.begin], at_end = ref_scan[nd.begin + nd.count];
+    const int nl = (int)(at_end.l - at_begin.l), nr = (int)(at_end.r - at_begin.r);
+    ANode L = nd, R = nd;
+    L.mx[d.axis] = d.plane;
+    R.mn[d.axis] = d.plane;
+    L.begin = (int)(at_begin.l + at_begin.r);
+    L.count = nl;
+    R.begin = L.begin + nl;
+    R.count = nr;
+    L.out = lo_out;
+    R.out = hi_out;
+    L.links[2 * d.axis + 1] = hi_out; // max face of the low child
+    R.links[2 * d.axis] = lo_out;     // min face of the high child
+    L.depth_left = R.depth_left = nd.depth_left - 1;
+    next_nodes[2 * rank] = L;
+    next_nodes[2 * rank + 1] = R;
+}
+
+__global__ void scatter_kernel(const ANode *__restrict__ nodes, const Decision *__restrict__ dec,
+                               const Triple *__restrict__ node_scan, const Triple *__restrict__ ref_scan,
+                               const int *__restrict__ ref_tri, const int *__restrict__ ref_node, int n_refs,
+                               const float *__restrict__ lo, const float *__restrict__ hi, int n_tris, int leaf_ref_base,
+                               int *__restrict__ next_tri, int *__restrict__ next_node, int *__restrict__ tri_indices) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_refs) return;
+    const int a = ref_node[i], t = ref_tri[i];
+    const Triple here = ref_scan[i];
+    const Triple fl = ref_flags(nodes, dec, ref_tri, ref_node, lo, hi, n_tris, i);
+    if (fl.f) {
+        tri_indices[leaf_ref_base + here.f] = t;
+        return;
+    }
+    const ANode &nd = nodes[a];
+    const Triple at_begin = ref_scan[nd.begin], at_end = ref_scan[nd.begin + nd.count];
+    const int child_base = (int)(at_begin.l + at_begin.r), nl = (int)(at_end.l - at_begin.l);
+    const int rank = (int)node_scan[a].l;
+    if (fl.l) {
+        const int p = child_base + (int)(here.l - at_begin.l);
+        next_tri[p] = t;
+        next_node[p] = 2 * rank;
+    }
+    if (fl.r) {
+        const int p = child_base + nl + (int)(here.r - at_begin.r);
+        next_tri[p] = t;
+        next_node[p] = 2 * rank + 1;
+    }
+}
+
+// ---- ropes -----------------------------------------------------------------------------
+// One thread per (node, face): a leaf's link is pushed down to the deepest node that the
+// whole face still looks into (kd_build.c: push_down_link with full = 1).
+__global__ void push_ropes_kernel(int *__restrict__ wire, int n_nodes) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int node = i / 6, face = i - node * 6;
+    if (node >= n_nodes) return;
+    int *w = wire + 17 * (size_t)node;
+    if (w[8] != 1) return;
+    int link = w[11 + face];
+    while (link != -1) {
+        const int *nb = wire + 17 * (size_t)link;
+        if (nb[8] == 1) break;
+        const int ax = nb[10];
+        if (face / 2 == ax) {
+            link = nb[(face & 1) ? 11 : 12];
+            continue;
+        }
+        const float plane = __int_as_float(nb[9]);
+        if (plane >= __int_as_float(w[4 + ax])) {
+            link = nb[11];
+        } else if (plane <= __int_as_float(w[ax])) {
+            link = nb[12];
+        } else {
+            break;
+        }
+    }
+    w[11 + face] = link;
+}
+
+template <typename T>
+void ensure(T *&ptr, size_t &cap, size_t want) {
+    if (want <= cap) return;
+    if (ptr) CU(cudaFree(ptr));
+    const size_t n = want + want / 4 + 1024;
+    CU(cudaMalloc((void **)&ptr, n * sizeof(T)));
+    cap = n;
+}
+
+// Working storage, kept between builds (an animated scene rebuilds every frame).
+struct Workspace {
+    float *lo = nullptr, *hi = nullptr;
+    size_t bounds_cap = 0, bounds_cap2 = 0;
+    int *ref_tri[2] = { nullptr, nullptr }, *ref_node[2] = { nullptr, nullptr };
+    size_t ref_cap[2][2] = { { 0, 0 }, { 0, 0 } };
+    ANode *nodes[2] = { nullptr, nullptr };
+    size_t node_cap[2] = { 0, 0 };
+    Decision *dec = nullptr;
+    size_t dec_cap = 0;
+    unsigned *hist = nullptr;
+    size_t hist_cap = 0;
+    Triple *ref_scan = nullptr, *node_scan = nullptr, *tiles = nullptr, *totals = nullptr;
+    size_t ref_scan_cap = 0, node_scan_cap = 0, tiles_cap = 0, totals_cap = 0;
+    int *box_keys = nullptr, *bad = nullptr;
+    size_t box_cap = 0, bad_cap = 0;
+    Triple *host_totals = nullptr; // pinned: [0] references, [1] nodes
+} W;
+
+template <typename F>
+void scan(int n, F f, Triple *out, Triple *total_dev, cudaStream_t s) {
+    const int tiles = std::max(1, (n + SCAN_TILE - 1) / SCAN_TILE);
+    ensure(W.tiles, W.tiles_cap, (size_t)tiles);
+    scan_tile_sums_kernel<<<tiles, SCAN_BLOCK, 0, s>>>(n, f, W.tiles);
+    scan_tile_offsets_kernel<<<1, 1024, 0, s>>>(W.tiles, tiles, total_dev);
+    scan_write_kernel<<<tiles, SCAN_BLOCK, 0, s>>>(n, f, W.tiles, total_dev, out);
+}
+
+} // namespace
+
+void clpt_gpu_build_release(void) {
+    auto drop = [](auto *&p) {
+        if (p) (void)cudaFree(p);
+        p = nullptr;
+    };
+    drop(W.lo), drop(W.hi), drop(W.ref_tri[0]), drop(W.ref_tri[1]), drop(W.ref_node[0]), drop(W.ref_node[1]);
+    drop(W.nodes[0]), drop(W.nodes[1]), drop(W.dec), drop(W.hist), drop(W.ref_scan), drop(W.node_scan);
+    drop(W.tiles), drop(W.totals), drop(W.box_keys), drop(W.bad);
+    if (W.host_totals) (void)cudaFreeHost(W.host_totals);
+    W = Workspace();
+}
+
+bool clpt_gpu_build(const float4 *verts, int n_verts, const int4 *corners, int n_tris, const ClptGpuBuildParams &P,
+                    ClptGpuTree &out, cudaStream_t s, char *err, size_t errlen) {
+    if (n_tris <= 0 || n_verts <= 0) {
+        snprintf(err, errlen, "empty mesh");
+        return false;
+    }
+    const int T = 256;
+    ensure(W.lo, W.bounds_cap, (size_t)n_tris * 3);
+    ensure(W.hi, W.bounds_cap2, (size_t)n_tris * 3);
+    ensure(W.box_keys, W.box_cap, (size_t)8);
+    ensure(W.bad, W.bad_cap, (size_t)1);
+    ensure(W.totals, W.totals_cap, (size_t)2);
+    if (!W.host_totals) CU(cudaMallocHost((void **)&W.host_totals, 2 * sizeof(Triple) + 64));
+    int *host_bad = reinterpret_cast<int *>(W.host_totals + 2);
+    CU(cudaMemsetAsync(W.bad, 0, sizeof(int), s));
+    tri_bounds_kernel<<<(n_tris + T - 1) / T, T, 0, s>>>(verts, corners, n_tris, n_verts, W.lo, W.hi, W.bad);
+    const int init_keys[6] = { INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN };
+    CU(cudaMemcpyAsync(W.box_keys, init_keys, sizeof(init_keys), cudaMemcpyHostToDevice, s));
+    scene_box_kernel<<<std::min(1024, (n_tris + T - 1) / T), T, 0, s>>>(W.lo, W.hi, n_tris, W.box_keys);
+    CU(cudaMemcpyAsync(host_bad, W.bad, sizeof(int), cudaMemcpyDeviceToHost, s));
+
+    int max_depth = P.max_depth;
+    if (max_depth <= 0) { // 8 + 1.3 log2(N), the usual bound for SAH kd-trees
+        int lg = 0;
+        while ((1 << lg) < n_tris) lg++;
+        max_depth = 8 + (13 * lg) / 10;
+    }
+    const int min_split = P.min_split > 1 ? P.min_split : 2;
+
+    int cur = 0;
+    ensure(W.ref_tri[0], W.ref_cap[0][0], (size_t)n_tris);
+    ensure(W.ref_node[0], W.ref_cap[0][1], (size_t)n_tris);
+    ensure(W.nodes[0], W.node_cap[0], (size_t)1);
+    root_kernel<<<(n_tris + T - 1) / T, T, 0, s>>>(W.box_keys, n_tris, max_depth, W.nodes[0], W.ref_tri[0], W.ref_node[0]);
+
+    // output arrays grow as the levels come in
+    size_t n_out = 1;        // wire nodes allocated so far (the root)
+    size_t n_leaf_refs = 0;  // tri_indices written so far
+    int n_nodes = 1, n_refs = n_tris;
+    ensure(out.wire, out.wire_cap, (size_t)17 * 1024);
+    int levels = 0;
+    while (n_nodes > 0) {
+        levels++;
+        ensure(W.dec, W.dec_cap, (size_t)n_nodes);
+        ensure(W.hist, W.hist_cap, (size_t)n_nodes * 3 * 2 * NBINS);
+        ensure(W.ref_scan, W.ref_scan_cap, (size_t)n_refs + 1);
+        ensure(W.node_scan, W.node_scan_cap, (size_t)n_nodes + 1);
+        CU(cudaMemsetAsync(W.hist, 0, (size_t)n_nodes * 3 * 2 * NBINS * sizeof(unsigned), s));
+        if (n_refs > 0) {
+            bin_kernel<<<(n_refs + 255) / 256, 256, 0, s>>>(W.nodes[cur], W.ref_tri[cur], W.ref_node[cur], n_refs, W.lo,
+                                                            W.hi, n_tris, min_split, W.hist);
+        }
+        choose_kernel<<<(n_nodes * 32 + 255) / 256, 256, 0, s>>>(W.nodes[cur], n_nodes, W.hist, min_split, P.ct, P.ci,
+                                                                   P.empty_bonus, W.dec);
+        RefFlagFn rf{ W.nodes[cur], W.dec, W.ref_tri[cur], W.ref_node[cur], W.lo, W.hi, n_tris };
+        scan(n_refs, rf, W.ref_scan, W.totals, s);
+        SplitFlagFn sf{ W.dec };
+        scan(n_nodes, sf, W.node_scan, W.totals + 1, s);
+        CU(cudaMemcpyAsync(W.host_totals, W.totals, 2 * sizeof(Triple), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        if (levels == 1 && *host_bad) {
+            snprintf(err, errlen, "triangle corner references a missing vertex");
+            return false;
+        }
+        const Triple rt = W.host_totals[0], nt = W.host_totals[1];
+        const int n_splits = (int)nt.l;
+        const size_t next_refs = (size_t)rt.l + rt.r, next_nodes = (size_t)2 * n_splits;
+        if (next_refs > 0x7fff0000u || n_out + next_nodes > 0x1fff0000u) {
+            snprintf(err, errlen, "tree too large (%zu references, %zu nodes)", next_refs, n_out + next_nodes);
+            return false;
+        }
+        // grow the outputs, keeping what is there
+        if ((n_out + next_nodes) * 17 > out.wire_cap) {
+            int *bigger = nullptr;
+            const size_t cap = (n_out + next_nodes) * 17 * 2;
+            CU(cudaMalloc((void **)&bigger, cap * sizeof(int)));
+            CU(cudaMemcpyAsync(bigger, out.wire, n_out * 17 * sizeof(int), cudaMemcpyDeviceToDevice, s));
+            CU(cudaStreamSynchronize(s));
+            CU(cudaFree(out.wire));
+            out.wire = bigger;
+            out.wire_cap = cap;
+        }
+        if (n_leaf_refs + rt.f > out.tri_indices_cap) {
+            int *bigger = nullptr;
+            const size_t cap = (n_leaf_refs + rt.f) * 2 + (size_t)n_tris;
+            CU(cudaMalloc((void **)&bigger, cap * sizeof(int)));
+            if (out.tri_indices) {
+                CU(cudaMemcpyAsync(bigger, out.tri_indices, n_leaf_refs * sizeof(int), cudaMemcpyDeviceToDevice, s));
+                CU(cudaStreamSynchronize(s));
+                CU(cudaFree(out.tri_indices));
+            }
+            out.tri_indices = bigger;
+            out.tri_indices_cap = cap;
+        }
+        const int nxt = cur ^ 1;
+        ensure(W.ref_tri[nxt], W.ref_cap[nxt][0], next_refs);
+        ensure(W.ref_node[nxt], W.ref_cap[nxt][1], next_refs);
+        ensure(W.nodes[nxt], W.node_cap[nxt], next_nodes);
+        emit_kernel<<<(n_nodes + T - 1) / T, T, 0, s>>>(W.nodes[cur], n_nodes, W.dec, W.node_scan, W.ref_scan, (int)n_out,
+                                                        (int)n_leaf_refs, out.wire, W.nodes[nxt]);
+        if (n_refs > 0) {
+            scatter_kernel<<<(n_refs + T - 1) / T, T, 0, s>>>(W.nodes[cur], W.dec, W.node_scan, W.ref_scan, W.ref_tri[cur],
+                                                              W.ref_node[cur], n_refs, W.lo, W.hi, n_tris,
+                                                              (int)n_leaf_refs, W.ref_tri[nxt], W.ref_node[nxt],
+                                                              out.tri_indices);
+        }
+        n_out += next_nodes;
+        n_leaf_refs += rt.f;
+        n_nodes = (int)next_nodes;
+        n_refs = (int)next_refs;
+        cur = nxt;
+    }
+    push_ropes_kernel<<<(unsigned)((n_out * 6 + T - 1) / T), T, 0, s>>>(out.wire, (int)n_out);
+    CU(cudaGetLastError());
+    out.n_nodes = (int)n_out;
+    out.n_refs = (int)n_leaf_refs;
+    out.levels = levels;
+    return true;
+}
+
+// ======================================================================================
+// Re-layout on the device: the twin of clpt_pack_scene (scene_pack.cpp).  Same numbering
+// (the children of the k-th split node in input order become nodes 1+2k and 2+2k; leaves
+// keep their input order), same records, same start-node table -- the two packers produce
+// the same bytes from the same wire arrays (tests/test_gpu_build.py).
+// ======================================================================================
+namespace {
+
+struct WireTypeFn { // .l counts split nodes, .f counts leaves, .r counts fat-leaf triangle slots
+    const int *wire;
+    __device__ Triple operator()(int i) const {
+        const int *w = wire + 17 * (size_t)i;
+        if (w[8] == 0) return Triple{ 1u, 0u, 0u };
+        return Triple{ 0u, w[10] >= CLPT_COOP_LEAF_MIN ? (unsigned)w[10] : 0u, 1u };
+    }
+};
+
+__global__ void renumber_kernel(const int *__restrict__ wire, int n_nodes, const Triple *__restrict__ scan,
+                                int *__restrict__ new_of) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    if (i == 0) new_of[0] = 0;
+    const int *w = wire + 17 * (size_t)i;
+    if (w[8] == 0) {
+        const int ks = (int)scan[i].l;
+        new_of[w[11]] = 1 + 2 * ks; // each child has one parent: no two threads write one slot
+        new_of[w[12]] = 2 + 2 * ks;
+    }
+}
+
+__global__ void pack_nodes_kernel(const int *__restrict__ wire, int n_nodes, const Triple *__restrict__ scan,
+                                  const int *__restrict__ new_of, uint2 *__restrict__ nodes, float4 *__restrict__ leaves) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const int *w = wire + 17 * (size_t)i;
+    const int ni = new_of[i];
+    if (w[8] == 0) {
+        nodes[ni] = make_uint2((unsigned)w[9], ((unsigned)new_of[w[11]] << 2) | (unsigned)w[10]);
+        return;
+    }
+    const int li = (int)scan[i].f;
+    nodes[ni] = make_uint2((unsigned)li, 0x80000003u);
+    const int count = w[10], first = count > 0 ? w[9] : 0;
+    float4 *L = leaves + 4 * (size_t)li;
+    L[0] = make_float4(__int_as_float(w[0]), __int_as_float(w[1]), __int_as_float(w[2]), __int_as_float(first));
+    L[1] = make_float4(__int_as_float(w[4]), __int_as_float(w[5]), __int_as_float(w[6]), __int_as_float(count));
+    int ropes[6];
+    for (int f = 0; f < 6; f++) {
+        const int r = w[11 + f];
+        if (r < 0 || r >= n_nodes) {
+            ropes[f] = -1;
+        } else if (wire[17 * (size_t)r + 8] == 1) {
+            ropes[f] = -2 - (int)scan[r].f; // straight to the leaf record
+        } else {
+            ropes[f] = new_of[r];
+        }
+    }
+    L[2] = make_float4(__int_as_float(ropes[0]), __int_as_float(ropes[1]), __int_as_float(ropes[2]),
+                       __int_as_float(ropes[3]));
+    L[3] = make_float4(__int_as_float(ropes[4]), __int_as_float(ropes[5]), 0.0f, 0.0f);
+}
+
+__global__ void pack_tris_kernel(const int *__restrict__ tri_indices, int n_refs, const int4 *__restrict__ corners,
+                                 const float4 *__restrict__ verts, float4 *__restrict__ tri) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_refs) return;
+    const int b = tri_indices[s];
+    const float4 v0 = verts[corners[3 * (size_t)b].x], v1 = verts[corners[3 * (size_t)b + 1].x],
+                 v2 = verts[corners[3 * (size_t)b + 2].x];
+    float4 *T = tri + 3 * (size_t)s;
+    T[0] = make_float4(v0.x, v0.y, v0.z, __int_as_float(b));
+    // one fp32 subtraction each, the same rounding as `v1 - v0` in the kernel
+    T[1] = make_float4(__fsub_rn(v1.x, v0.x), __fsub_rn(v1.y, v0.y), __fsub_rn(v1.z, v0.z), 0.0f);
+    T[2] = make_float4(__fsub_rn(v2.x, v0.x), __fsub_rn(v2.y, v0.y), __fsub_rn(v2.z, v0.z), 0.0f);
+}
+
+struct LutGrid {
+    double root_min[3], ext[3], scale[3]; // scale = (double)(float)(dim / ext), as the host packer reads it back
+    int dim[3];
+};
+
+// Start-node table: per cell, follow the branches the whole (slightly enlarged) cell is
+// forced to take from the root (scene_pack.cpp, "start-node table").
+__global__ void pack_lut_kernel(const int *__restrict__ wire, const int *__restrict__ new_of, const LutGrid G,
+                                int *__restrict__ lut) {
+    const size_t total = (size_t)G.dim[0] * G.dim[1] * G.dim[2];
+    const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= total) return;
+    const int c[3] = { (int)(cell % G.dim[0]), (int)((cell / G.dim[0]) % G.dim[1]),
+                       (int)(cell / ((size_t)G.dim[0] * G.dim[1])) };
+    double lo[3], hi[3];
+    for (int a = 0; a < 3; a++) {
+        const double sc = G.scale[a];
+        const double margin = 1e-5 * (1.0 + G.ext[a] + fabs(G.root_min[a]));
+        if (sc > 0) {
+            lo[a] = G.root_min[a] + c[a] / sc - margin;
+            hi[a] = G.root_min[a] + (c[a] + 1) / sc + margin;
+        } else {
+            lo[a] = -1e300;
+            hi[a] = 1e300;
+        }
+        if (c[a] == 0) lo[a] = -1e300;
+        if (c[a] == G.dim[a] - 1) hi[a] = 1e300;
+    }
+    int o = 0;
+    for (;;) {
+        const int *w = wire + 17 * (size_t)o;
+        if (w[8] != 0) break;
+        const int ax = w[10];
+        const double plane = (double)__int_as_float(w[9]);
+        if (hi[ax] <= plane) {
+            o = w[11];
+        } else if (lo[ax] > plane) {
+            o = w[12];
+        } else {
+            break;
+        }
+    }
+    lut[cell] = new_of[o];
+}
+
+int *g_new_of = nullptr;
+size_t g_new_of_cap = 0;
+Triple *g_wire_scan = nullptr;
+size_t g_wire_scan_cap = 0;
+
+} // namespace
+
+bool clpt_gpu_pack(const ClptGpuTree &tree, const float4 *verts, const int4 *corners, int n_prims, ClptGpuPacked &out,
+                   cudaStream_t s, char *err, size_t errlen) {
+    (void)n_prims;
+    const int n = tree.n_nodes, T = 256;
+    if (n <= 0) {
+        snprintf(err, errlen, "empty node array");
+        return false;
+    }
+    ensure(g_new_of, g_new_of_cap, (size_t)n);
+    ensure(g_wire_scan, g_wire_scan_cap, (size_t)n + 1);
+    ensure(W.totals, W.totals_cap, (size_t)2);
+    if (!W.host_totals) CU(cudaMallocHost((void **)&W.host_totals, 2 * sizeof(Triple) + 64));
+    WireTypeFn tf{ tree.wire };
+    scan(n, tf, g_wire_scan, W.totals, s);
+    CU(cudaMemcpyAsync(W.host_totals, W.totals, sizeof(Triple), cudaMemcpyDeviceToHost, s));
+    float box[8];
+    CU(cudaMemcpyAsync(box, tree.wire, sizeof(box), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    const int n_splits = (int)W.host_totals[0].l, n_leaves = (int)W.host_totals[0].f;
+    out.fat_refs = W.host_totals[0].r;
+    out.n_nodes = 1 + 2 * n_splits;
+    out.n_leaves = n_leaves;
+    out.n_refs = tree.n_refs;
+    ensure(out.nodes, out.nodes_cap, (size_t)out.n_nodes);
+    ensure(out.leaves, out.leaves_cap, (size_t)n_leaves * 4);
+    ensure(out.tri, out.tri_cap, (size_t)std::max(tree.n_refs, 1) * 3);
+    renumber_kernel<<<(n + T - 1) / T, T, 0, s>>>(tree.wire, n, g_wire_scan, g_new_of);
+    pack_nodes_kernel<<<(n + T - 1) / T, T, 0, s>>>(tree.wire, n, g_wire_scan, g_new_of, out.nodes, out.leaves);
+    if (tree.n_refs > 0) {
+        pack_tris_kernel<<<(tree.n_refs + T - 1) / T, T, 0, s>>>(tree.tri_indices, tree.n_refs, corners, verts, out.tri);
+    }
+    // start-node table geometry: the host packer's arithmetic (scene_pack.cpp), so that both give the same table
+    LutGrid G;
+    double vol = 1.0;
+    for (int a = 0; a < 3; a++) {
+        out.root_min[a] = box[a];
+        out.root_max[a] = box[4 + a];
+        G.root_min[a] = (double)box[a];
+        G.ext[a] = (double)box[4 + a] - (double)box[a];
+        if (!(G.ext[a] > 0)) G.ext[a] = 0;
+        vol *= G.ext[a] > 0 ? G.ext[a] : 1.0;
+    }
+    double target_cells = (double)n / 2;
+    target_cells = n < 64 ? 1.0 : (target_cells < 4096.0 ? 4096.0 : (target_cells > 2097152.0 ? 2097152.0 : target_cells));
+    const double cell = cbrt(vol / target_cells);
+    size_t total = 1;
+    for (int a = 0; a < 3; a++) {
+        int d = G.ext[a] > 0 && cell > 0 ? (int)ceil(G.ext[a] / cell) : 1;
+        d = d < 1 ? 1 : (d > 1024 ? 1024 : d);
+        out.lut_dim[a] = G.dim[a] = d;
+        out.lut_scale[a] = G.ext[a] > 0 ? (float)(d / G.ext[a]) : 0.0f;
+        G.scale[a] = (double)out.lut_scale[a];
+        total *= (size_t)d;
+    }
+    ensure(out.lut, out.lut_cap, total);
+    pack_lut_kernel<<<(unsigned)((total + T - 1) / T), T, 0, s>>>(tree.wire, g_new_of, G, out.lut);
+    CU(cudaGetLastError());
+    return true;
+}

@@ -172,11 +172,28 @@ __device__ __forceinline__ V3 trace_sample_coop(const ClptScene &S, const ClptFr
     return mk(fadd(fmul(k, col.x), str), fadd(fmul(k, col.y), str), fadd(fmul(k, col.z), str));
 }
 
+// Barrier among the G warps that share a pixel (named barrier 1 + group; __syncwarp for G = 1).
+__device__ __forceinline__ void group_sync(int log2_g, int group) {
+    if (log2_g == 0) {
+        __syncwarp();
+    } else {
+        asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(32 << log2_g) : "memory");
+    }
+}
+
 template <int MODE, bool COUNT, bool COOP>
 __global__ void __launch_bounds__(256, COOP ? CLPT_COOP_MIN_BLOCKS : CLPT_MIN_BLOCKS)
 render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptFrame F) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int log2_s = F.log2_sample_lanes, s_lanes = 1 << log2_s;
+    // Warps per pixel.  At >= 64 spp a pixel's samples are spread over G = 2, 4 or 8 warps of
+    // the block (32 samples each, side by side) instead of being walked by one warp in
+    // several rounds: a claim is then 1/G as long, which is what the END of a frame is made
+    // of (the last claims run while the rest of the GPU idles; on 8 GPUs a frame is only
+    // ~27 claims per warp long).  The warps of a group share the claim and the staging
+    // rows; the group's first warp does the ordered sum.  G = 1 is the plain scheme.
+    const int log2_g = F.log2_warps_per_pixel, g_warps = 1 << log2_g;
+    const int group = warp >> log2_g, member = warp & (g_warps - 1);
     int tw, th;
     warp_tile_dims(5 - log2_s, tw, th);
     const int pslot = lane >> log2_s, sslot = lane & (s_lanes - 1);
@@ -187,9 +204,13 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
     // summed in ascending sample order by one lane per channel (lane c of the pixel's
     // group sums channel c; with fewer than 4 lanes per pixel, lane 0 sums all three).
     // Same additions in the same order as a serial loop over the samples.
-    __shared__ float stage[8][3][33]; // [warp][channel][lane], rows padded against bank conflicts
+    // Rows: [warp group][channel][32 * G samples + 1], padded against bank conflicts.
+    __shared__ float stage[8 * 3 * 33];
+    const int row_len = 32 * g_warps + 1;
+    float *const my_stage = stage + group * 3 * row_len; // this group's three channel rows
+    const int my_col = member * 32 + lane;               // this lane's column in them
     const bool per_channel = s_lanes >= 4;
-    // Persistent warps: the grid only fills the machine; every warp claims warp tiles
+    // Persistent warps: the grid only fills the machine; every warp (group) claims warp tiles
     // from a global counter until none are left.  Blocks cost anything from nothing
     // (sky) to hundreds of microseconds (grazing ground), and with one tile per warp
     // fixed at launch the last heavy blocks left most SMs idle at the end of a frame
@@ -204,28 +225,35 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
     // rows.  Screen order is kept either way: neighbouring claims stay neighbours in the
     // tree (sorting rows by cost outright was measured and loses more in locality than it
     // wins, profiles/r01_experiments.json).
-    __shared__ unsigned tile_t0[8], tile_row[8]; // kept out of registers across the trace
+    __shared__ unsigned tile_t0[8], tile_row[8], tile_claim[8]; // kept out of registers across the trace
     const unsigned bx_count = (unsigned)F.blocks_x, n_tiles = (unsigned)F.n_warp_tiles;
     for (;;) {
         unsigned t = 0;
-        if (lane == 0) {
+        if (lane == 0 && member == 0) {
             t = atomicAdd(F.work_counter, 1u);
             tile_t0[warp] = (unsigned)clock();
+            tile_claim[group] = t;
         }
-        t = __shfl_sync(0xffffffffu, t, 0);
+        if (log2_g == 0) {
+            t = __shfl_sync(0xffffffffu, t, 0);
+        } else {
+            group_sync(log2_g, group);
+            t = tile_claim[group];
+        }
         if (t >= n_tiles) break;
         if (F.flags & CLPT_F_REVERSE) t = n_tiles - 1u - t;
         const unsigned w = t & 7u, b = t >> 3;
         const int bx = (int)(b % bx_count), by = (int)(b / bx_count);
-        if (lane == 0) tile_row[warp] = (unsigned)by;
+        if (lane == 0 && member == 0) tile_row[warp] = (unsigned)by;
         const int x = (bx * 4 + (int)(w & 3u)) * tw + (pslot & (tw - 1));
         const int ly = (by * 2 + (int)(w >> 2)) * th + pslot / tw; // row within this rank's slab
         const int y = slab_row_to_image_row(F, ly);
         const bool valid = x < F.width && y < F.height && ly < F.local_rows;
         const unsigned pixel = (unsigned)(y * F.width + x);
         V3 acc = mk(0.0f, 0.0f, 0.0f); // per_channel: only .x is used, for channel `sslot`
-        for (int base = 0; base < spp; base += s_lanes) {
-            const int s = base + sslot;
+        const int round_samples = s_lanes << log2_g;
+        for (int base = 0; base < spp; base += round_samples) {
+            const int s = base + (member << log2_s) + sslot; // (member > 0 only when s_lanes == 32)
             V3 colour = mk(0.0f, 0.0f, 0.0f);
             if (valid && s == 0 && F.aov_prim != nullptr && F.depth <= 0) {
                 // nothing is traced: the AOVs say "miss" instead of keeping the previous frame's
@@ -241,33 +269,37 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
                 colour = trace_sample<MODE, COUNT>(S, F, x, y, pixel, F.sample_base + (unsigned)s,
                                                    s == 0 && F.aov_prim != nullptr, cn);
             }
-            stage[warp][0][lane] = colour.x;
-            stage[warp][1][lane] = colour.y;
-            stage[warp][2][lane] = colour.z;
-            __syncwarp();
-            const int in_round = min(s_lanes, spp - base);
-            if (per_channel) {
-                if (sslot < 3) {
-                    const float *src = &stage[warp][sslot][group_base];
-                    for (int j = 0; j < in_round; j++) acc.x = fadd(acc.x, src[j]);
-                }
-            } else if (sslot == 0) {
-                for (int j = 0; j < in_round; j++) {
-                    acc = vadd(acc, mk(stage[warp][0][group_base + j], stage[warp][1][group_base + j],
-                                       stage[warp][2][group_base + j]));
+            my_stage[0 * row_len + my_col] = colour.x;
+            my_stage[1 * row_len + my_col] = colour.y;
+            my_stage[2 * row_len + my_col] = colour.z;
+            group_sync(log2_g, group);
+            const int in_round = min(round_samples, spp - base);
+            if (member == 0) {
+                if (per_channel) {
+                    if (sslot < 3) {
+                        const float *src = my_stage + sslot * row_len + group_base;
+                        for (int j = 0; j < in_round; j++) acc.x = fadd(acc.x, src[j]);
+                    }
+                } else if (sslot == 0) {
+                    for (int j = 0; j < in_round; j++) {
+                        acc = vadd(acc, mk(my_stage[0 * row_len + group_base + j], my_stage[1 * row_len + group_base + j],
+                                           my_stage[2 * row_len + group_base + j]));
+                    }
                 }
             }
-            __syncwarp();
+            group_sync(log2_g, group);
         }
-        if (per_channel) { // bring the three channel sums to the group's first lane
-            const float r = __shfl_sync(0xffffffffu, acc.x, group_base);
-            const float g = __shfl_sync(0xffffffffu, acc.x, group_base + 1);
-            const float bl = __shfl_sync(0xffffffffu, acc.x, group_base + 2);
-            acc = mk(r, g, bl);
-        }
-        if (valid && sslot == 0) store_pixel(F, x, ly, acc, spp);
-        if (lane == 0 && F.row_cost) {
-            atomicAdd(F.row_cost + tile_row[warp], (unsigned long long)((unsigned)clock() - tile_t0[warp]));
+        if (member == 0) {
+            if (per_channel) { // bring the three channel sums to the group's first lane
+                const float r = __shfl_sync(0xffffffffu, acc.x, group_base);
+                const float g = __shfl_sync(0xffffffffu, acc.x, group_base + 1);
+                const float bl = __shfl_sync(0xffffffffu, acc.x, group_base + 2);
+                acc = mk(r, g, bl);
+            }
+            if (valid && sslot == 0) store_pixel(F, x, ly, acc, spp);
+            if (lane == 0 && F.row_cost) {
+                atomicAdd(F.row_cost + tile_row[warp], (unsigned long long)((unsigned)clock() - tile_t0[warp]));
+            }
         }
     }
     if (COUNT) {

@@ -111,6 +111,29 @@ void CLSetMeshesRaw(const void *nodes, size_t node_bytes,
                     const void *tris, size_t tri_bytes,
                     const void *verts, size_t vert_bytes,
                     const void *norms, size_t norm_bytes);
+/* Device-side scene preparation (no counterpart in the
+ * reference, whose tree is built on the host by src/kd_tree.c:202-276 before
+ * CLSetMeshes): the mesh -- verts 16 B each, three 16-byte corners {v, vn, vt, 0} per
+ * triangle, optional normals; the lists LoadModel produces (src/model.c:74-145) -- is
+ * uploaded once, a binned-SAH kd-tree with ropes is built ON THE DEVICE in the
+ * reference's wire format and re-laid-out there for traversal.  Nothing is owned; the
+ * data is copied.  The build is deterministic: the same mesh gives the same tree,
+ * byte for byte, on every GPU.  CLSetBuildParams: max_depth <= 0 means
+ * 8 + 1.3 log2(triangles); the cost constants are build_kd_sah's. */
+void CLBuildMeshes(const void *verts, size_t vert_bytes, const void *tris, size_t tri_bytes,
+                   const void *norms, size_t norm_bytes);
+void CLSetBuildParams(int max_depth, int min_split, float traversal_cost, float intersect_cost,
+                      float empty_bonus);
+void CLLastBuildMs(float *build_ms, float *pack_ms); /* device time of the last CLBuildMeshes */
+void CLBuildStats(int *nodes, int *tri_refs, int *levels);
+/* The tree CLBuildMeshes built, as a regular `kd` (fresh host lists the caller owns and
+ * frees with delete_kd): what the oracle walks in the parity tests, and what write_kd
+ * can cache. */
+void CLDownloadKd(kd *out);
+/* Test hook: the traversal layout in device memory, which = 0 nodes, 1 leaf records,
+ * 2 triangle slots, 3 start-node table.  Returns the size in bytes; copies when dst is
+ * large enough. */
+size_t CLDebugReadPacked(int which, void *dst, size_t bytes);
 void CLSetMaterials(const CLMaterial *materials, size_t material_bytes,
                     const int *tri_material, size_t tri_material_bytes);
 /* mode, depth (= bounces + 1; the reference passes 2, src/kernel.cl:468),

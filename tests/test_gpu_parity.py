@@ -209,6 +209,27 @@ def test_jittered_multisample(clpt, oracle, renderer, scene_cache):
     assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("spp,engine", [(64, 1), (130, 1), (300, 1), (64, 2), (33, 1)])
+def test_samples_spread_over_warps(clpt, oracle, renderer, scene_cache, spp, engine):
+    """At >= 64 spp the samples of a pixel are traced by 2, 4 or 8 warps side by side and summed
+    by the first of them in ascending sample order: the image does not depend on the spread
+    (64 -> 2 warps, one round; 130 -> 4 warps, a full round and one of 2 samples; 300 -> 8
+    warps; 33 -> one warp, two rounds)."""
+    scene, _ = scene_cache("hf22n")
+    w, h = 61, 37
+    cam = _cam(clpt, "canonical", h)
+    kw = dict(mode=1, depth=4, spp=spp, seed=3, flags=clpt.FLAG_JITTER)
+    L = clpt.lib()
+    try:
+        L.CLSetEngine(engine)
+        img, prim, t, uv = _render_gpu(renderer, scene, cam, w, h, **kw)
+    finally:
+        L.CLSetEngine(0)
+    ref = oracle.render(scene, cam, w, h, **kw)
+    assert np.array_equal(prim, ref["prim"])
+    _assert_bit_equal(img, ref["rgba"], f"{spp} spp")
+
+
 def test_path_mode_extension(clpt, oracle, renderer, scene_cache):
     """Mode C (no reference behaviour): identical Philox streams -> identical images."""
     from clpathtracer_b200 import scenes
