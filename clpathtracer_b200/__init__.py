@@ -112,6 +112,7 @@ def lib() -> C.CDLL:
         "CLBuildMeshes": (None, [vp, sz, vp, sz, vp, sz]), "CLSetBuildParams": (None, [i, i, f, f, f]),
         "CLLastBuildMs": (None, [C.POINTER(f), C.POINTER(f)]), "CLBuildStats": (None, [C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
         "CLDownloadKd": (None, [C.POINTER(KD)]), "CLDebugReadPacked": (sz, [i, vp, sz]),
+        "CLUpdateVertices": (None, [sz, vp, sz]), "CLRebuildMeshes": (None, []),
         "CLDeleteImage": (None, []), "CLCreateImage": (None, [u]), "CLExecute": (None, [i, i]),
         "CLSelectDevice": (None, [i]), "CLSetRenderParams": (None, [i, i, i, u, i]),
         "CLSetMaxLeafVisits": (None, [i]), "CLSetEngine": (None, [i]), "CLLastEngine": (i, []), "CLCreateImageHeadless": (None, [i, i]),
@@ -125,7 +126,12 @@ def lib() -> C.CDLL:
         "CLDeviceName": (C.c_char_p, []), "CLDeviceSMCount": (i, []),
     }
     for name, (res, args) in sig.items():
-        fn = getattr(L, name)
+        try:
+            fn = getattr(L, name)
+        except AttributeError:
+            if os.environ.get("CLPT_LIB"):  # an experimental / older build selected on purpose: bind what it has
+                continue
+            raise
         fn.restype, fn.argtypes = res, args
     _lib = L
     return L
@@ -313,6 +319,14 @@ class Renderer:
         n4 = _as_vec4(norms) if norms is not None and len(norms) else None
         self.L.CLBuildMeshes(v4.ctypes.data, v4.nbytes, c4.ctypes.data, c4.nbytes,
                              None if n4 is None else n4.ctypes.data, 0 if n4 is None else n4.nbytes)
+
+    def update_vertices(self, first: int, verts: np.ndarray) -> None:
+        """Overwrite vertices [first, first + len(verts)) of the mesh uploaded by build_meshes."""
+        v4 = _as_vec4(verts)
+        self.L.CLUpdateVertices(int(first), v4.ctypes.data, v4.nbytes)
+
+    def rebuild_meshes(self) -> None:
+        self.L.CLRebuildMeshes()
 
     def download_kd(self) -> "Scene":
         """The device-built tree as a Scene (wire format) for the oracle."""

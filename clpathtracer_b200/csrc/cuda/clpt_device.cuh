@@ -57,9 +57,8 @@ struct ClptScene {
 };
 
 #define CLPT_MAX_PEERS 8
-// Leaves with at least this many triangles are shared between the lanes of a warp by the
-// cooperative engine (clpt_trace.cuh: closest_hit_coop); also the "fat leaf" of the
-// automatic engine choice.
+// A "fat" leaf for the automatic engine choice: trees whose triangle slots mostly live in
+// leaves of at least this many triangles are rendered by engine 2.
 #define CLPT_COOP_LEAF_MIN 8
 
 struct ClptFrame {
@@ -89,6 +88,9 @@ struct ClptFrame {
     // row_cost[its block row] (null = not recorded); CLExecute looks at where one frame's
     // cost sits and points the next frame's claims so that they END at the cheap side.
     unsigned long long *row_cost;
+    // Claim order: when set, the k-th row of blocks claimed is screen row row_order[k] (the
+    // previous frame's costliest rows first, csrc/host/frame_sched.c) and CLPT_F_REVERSE is unused.
+    const int *row_order;
     int blocks_x, n_warp_tiles;   // filled in by clpt_launch_render
 };
 
@@ -100,7 +102,7 @@ __device__ __forceinline__ unsigned clpt_to_unorm8(float v) {
 #endif
 
 enum { CLPT_F_JITTER = 1, CLPT_F_ACCUMULATE = 2, CLPT_F_COUNTERS = 4, CLPT_F_REVERSE = 0x100 /* internal */,
-       CLPT_F_COOP = 0x200 /* internal: warp-cooperative leaves (engine 2) */ };
+       CLPT_F_FAT = 0x200 /* internal: engine 2, the kernel compiled for fewer resident blocks (fat leaves) */ };
 
 // render_kernel.cu
 void clpt_launch_render(const ClptScene &scene, const ClptFrame &frame, int sm_count, cudaStream_t stream);
@@ -116,5 +118,7 @@ struct ClptFlagPeers {
 // array is written by src only.  Epochs only grow.
 void clpt_launch_flag_barrier(const ClptFlagPeers &peers, int rank, int nranks, unsigned int epoch,
                               cudaStream_t stream);
-void clpt_launch_pack_rgba8(const float4 *src, uchar4 *dst, size_t n, cudaStream_t stream);
+void clpt_launch_pack_rgba8(const float4 *src, uchar4 *dst, size_t n, bool normalise, cudaStream_t stream);
+void clpt_launch_deinterleave_rgba8(const uchar4 *gathered, uchar4 *image, int width, int height, int nranks,
+                                    int tile_rows, int slab_rows, cudaStream_t stream);
 const void *clpt_render_kernel_symbol(void);

@@ -19,8 +19,13 @@
 #define CLPT_MIN_BLOCKS 8 // resident 256-thread blocks per SM the register allocation aims for (measured: 3 -> 2029, 4 -> 2488, 6 -> 2921, 8 -> 3054 Mrays/s)
 #endif
 
-#ifndef CLPT_COOP_MIN_BLOCKS
-#define CLPT_COOP_MIN_BLOCKS 5 // the cooperative engine is arithmetic-bound on fat leaves: 48 registers, no spills
+#ifndef CLPT_FAT_MIN_BLOCKS
+// Engine 2, for trees with fat leaves (the reference builder's DEPTH-15 trees: ~56 triangles per
+// leaf at 1M triangles): the same code compiled for fewer resident blocks.  Such frames are short
+// and end with a few warps walking the grazing rays of the horizon (thousands of triangle tests
+// each), so what counts is how fast ONE warp runs, not how many are resident (measured,
+// profiles/r02_experiments.json).
+#define CLPT_FAT_MIN_BLOCKS 4
 #endif
 
 namespace {
@@ -80,9 +85,7 @@ struct Counters {
 
 // ---- the four steps of the traversal, src/kernel.cl:311-389 ----------------
 // They are separate functions because two kernels compose them differently: the
-// lane-per-ray engine runs one ray to completion per call (closest_hit below), the
-// warp-cooperative engine keeps the 32 lanes of a warp in one loop and shares the
-// triangle runs of fat leaves between them (closest_hit_coop).
+// render kernel runs one ray to completion per call (closest_hit below).
 
 // Root clip, kernel.cl:101-144.  False when the ray misses the scene box.
 __device__ __forceinline__ bool root_clip(const ClptScene &S, V3 o, V3 inv, float &tmin, float &tmax) {
@@ -262,122 +265,6 @@ __device__ __forceinline__ Hit closest_hit(const ClptScene &S, V3 o, V3 d, int m
         // (the box is re-read from L1 rather than kept live across the run)
         if (h.ref >= 0 && hit_is_final(h.ref, leaf_entry(__ldg(L), __ldg(L + 1), o, inv), min_hit)) break;
         if (leave_leaf<COUNT>(nodes, L, far, o, d, tmax, max_visits, p1, n, visits, cn)) break;
-    }
-    h.t = min_hit;
-    return h;
-}
-
-// ---- warp-cooperative traversal (engine 2) ----------------------------------
-// Trees built by the reference's own builder stop at DEPTH 15 (src/kd_tree.c:8-9): at
-// a million triangles a leaf holds ~56 of them and a ray makes ~265 Moller-Trumbore
-// tests, so the triangle run IS the frame.  With one lane per
-// ray, the lanes of a warp that sit in different leaves serialise their runs, and one
-// long grazing ray keeps its whole warp (and the end of the frame) waiting.  Here the
-// 32 lanes stay in ONE loop -- descend, leaf, exit -- and a leaf with at least
-// CLPT_COOP_MIN triangles is not walked by its own lane: its ray is broadcast and the
-// run is spread over the warp, 32 triangles per step (the same test, the same
-// operands), followed by an ordered reduction that reproduces the serial loop's
-// result: the smallest t wins, and among equal t the LAST triangle (src/kernel.cl:344,
-// `t <= minHit`).  A positive float orders like its bit pattern, so the reduction is two
-// integer warp reductions (redux.sync).  Small leaves are still walked per lane.
-#ifndef CLPT_COOP_MIN
-#define CLPT_COOP_MIN CLPT_COOP_LEAF_MIN
-#endif
-
-// One Moller-Trumbore test (kernel.cl:227-255) of triangle slot i; returns the bit
-// pattern of t for an accepted hit, 0xffffffff otherwise.
-__device__ __forceinline__ unsigned triangle_test_bits(const float4 *__restrict__ tri, int i, V3 o, V3 d) {
-    const V3 e1 = xyz(__ldg(tri + 3 * (size_t)i + 1));
-    const V3 e2 = xyz(__ldg(tri + 3 * (size_t)i + 2));
-    const V3 pvec = vcross(d, e2);
-    const float det = vdot(e1, pvec);
-    if (det < 0.0f) return 0xffffffffu;
-    const float idet = frcp(det);
-    const V3 tvec = vsub(o, xyz(__ldg(tri + 3 * (size_t)i)));
-    const float u = fmul(vdot(tvec, pvec), idet);
-    if (u < 0.0f || u > 1.0f) return 0xffffffffu;
-    const V3 qvec = vcross(tvec, e1);
-    const float v = fmul(vdot(d, qvec), idet);
-    if (v < 0.0f || fadd(u, v) > 1.0f) return 0xffffffffu;
-    const float t = fmul(vdot(e2, qvec), idet);
-    if (!(t > 0.0f)) return 0xffffffffu;
-    return __float_as_uint(t);
-}
-
-// All 32 lanes of the warp call this together; `live` says whether the lane has a ray.
-template <bool COUNT>
-__device__ __forceinline__ Hit closest_hit_coop(const ClptScene &S, V3 o, V3 d, bool live, int max_visits,
-                                                Counters &cn) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    Hit h;
-    h.ref = -1;
-    h.t = 0.0f;
-    if (COUNT && live) cn.rays++;
-    const V3 inv = mk(frcp(d.x), frcp(d.y), frcp(d.z));
-    float tmin, tmax = 0.0f;
-    if (live && !root_clip(S, o, inv, tmin, tmax)) live = false;
-    V3 p1 = o;
-    if (live && tmin > 0.0f) p1 = vadd(p1, vscale(d, tmin));
-    int visits = 0;
-    float min_hit = 0.0f;
-    const uint2 *__restrict__ nodes = S.nodes;
-    uint2 n = make_uint2(0u, 0u);
-    if (live) n = __ldg(nodes + (COUNT ? 0 : start_node(S, p1)));
-    while (__any_sync(FULL, live)) {
-        const float4 *L = S.leaves;
-        int first = 0, count = 0, far = 0;
-        if (live) {
-            n = descend<COUNT>(nodes, n, p1, cn);
-            if (COUNT) cn.leaves++;
-            L = S.leaves + 4 * (size_t)n.x;
-            const float4 lmin = __ldg(L), lmax = __ldg(L + 1);
-            leaf_exit(lmin, lmax, o, inv, tmax, far);
-            first = __float_as_int(lmin.w);
-            count = __float_as_int(lmax.w);
-        }
-        const bool fat = live && count >= CLPT_COOP_MIN;
-        if (live && !fat) triangle_run<COUNT>(S.tri, first, count, o, d, h.ref, min_hit, cn);
-        unsigned todo = __ballot_sync(FULL, fat);
-        while (todo) { // one fat leaf at a time, its ray broadcast to the warp
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const V3 ro = mk(__shfl_sync(FULL, o.x, src), __shfl_sync(FULL, o.y, src), __shfl_sync(FULL, o.z, src));
-            const V3 rd = mk(__shfl_sync(FULL, d.x, src), __shfl_sync(FULL, d.y, src), __shfl_sync(FULL, d.z, src));
-            const int rf = __shfl_sync(FULL, first, src), rc = __shfl_sync(FULL, count, src);
-            unsigned best = 0xffffffffu;
-            int best_i = -1;
-            for (int base = 0; base < rc; base += 32) {
-                const int i = base + lane;
-                unsigned bits = 0xffffffffu;
-                if (i < rc) {
-                    if (COUNT) cn.tris++;
-                    bits = triangle_test_bits(S.tri, rf + i, ro, rd);
-                }
-                const unsigned m = __reduce_min_sync(FULL, bits);
-                if (m != 0xffffffffu) {
-                    const int last = __reduce_max_sync(FULL, bits == m ? i : -1);
-                    if (m <= best) { // a later chunk wins ties, like a later triangle
-                        best = m;
-                        best_i = last;
-                    }
-                }
-            }
-            if (lane == src && best_i >= 0) {
-                const float t = __uint_as_float(best);
-                if (h.ref < 0 || t <= min_hit) {
-                    min_hit = t;
-                    h.ref = rf + best_i;
-                }
-            }
-        }
-        if (live) {
-            if (h.ref >= 0 && hit_is_final(h.ref, leaf_entry(__ldg(L), __ldg(L + 1), o, inv), min_hit)) {
-                live = false;
-            } else if (leave_leaf<COUNT>(nodes, L, far, o, d, tmax, max_visits, p1, n, visits, cn)) {
-                live = false;
-            }
-        }
     }
     h.t = min_hit;
     return h;

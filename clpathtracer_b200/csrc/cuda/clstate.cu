@@ -141,7 +141,8 @@ struct {
     ClptGpuBuildParams build_params;
     ClptGpuTree gpu_tree;
     ClptGpuPacked gpu_packed;
-    bool scene_on_gpu = false;
+    bool scene_on_gpu = false; // the traversal layout in use is gpu_packed
+    bool mesh_on_gpu = false;  // verts/corners hold a mesh uploaded by CLBuildMeshes
     float last_build_ms = 0, last_pack_ms = 0;
     DevBuf<unsigned char> objects;
     int objcount = 0;
@@ -159,6 +160,7 @@ struct {
     int width = 0, height = 0;
     bool headless = false, have_image = false;
     DevBuf<float4> image, slab, gathered, scratch;
+    DevBuf<uchar4> slab8, gathered8; // texel twins of slab / gathered (progressive read-back across GPUs)
     bool aov = false;
     DevBuf<int> aov_prim;
     DevBuf<float> aov_t;
@@ -172,6 +174,9 @@ struct {
     int row_count = 0;         // rows the current direction was measured on
     long long row_key[8] = {}; // ... and under which image / sharding / parameters
     bool claim_reverse = false;
+    DevBuf<int> row_order;        // claim order of the next frame (hot rows first), see frame_sched.c
+    int *host_row_order = nullptr; // pinned
+    bool have_row_order = false;
     unsigned long long frames_rendered = 0;
     unsigned long long host_counters[6] = { 0 };
     float last_kernel_ms = 0;
@@ -188,7 +193,7 @@ struct {
         unsigned long long ticket = 0;
     } rd[2];
     unsigned long long rd_issued = 0;
-    int engine = 0;      // 0 auto, 1 lane-per-ray leaves, 2 warp-cooperative leaves
+    int engine = 0;      // 0 auto, 1 full occupancy, 2 fat-leaf variant (fewer resident blocks)
     int auto_engine = 1; // what "auto" means for the current tree (decided in upload_scene)
     int last_engine = 1;
 
@@ -271,7 +276,7 @@ void upload_scene(const kdnode *nodes, size_t node_bytes, const int *tri_indices
     }
     // per-triangle materials belong to the previous mesh
     St.tri_material.release();
-    St.scene_on_gpu = false;
+    St.scene_on_gpu = St.mesh_on_gpu = false; // (the corner buffer now belongs to this scene)
     ClptScene &S = St.scene;
     S.n_nodes = packed.n_nodes;
     S.n_leaves = packed.n_leaves;
@@ -285,8 +290,8 @@ void upload_scene(const kdnode *nodes, size_t node_bytes, const int *tri_indices
     }
     rebuild_scene_struct();
     St.have_scene = true;
-    // "automatic" engine for this tree: warp-cooperative leaves when most triangle slots
-    // live in fat leaves (the reference builder's DEPTH-15 trees at >= ~50k triangles)
+    // "automatic" engine for this tree: the fat-leaf variant when most triangle slots live in
+    // fat leaves (the reference builder's DEPTH-15 trees at >= ~50k triangles)
     {
         size_t fat_refs = 0;
         for (int l = 0; l < packed.n_leaves; l++) {
@@ -566,13 +571,25 @@ void enqueue_read(void *dst, size_t bytes, int format) {
     if (!St.copy_stream) CU(cudaStreamCreateWithFlags(&St.copy_stream, cudaStreamNonBlocking));
     // the copy that last used this staging buffer must have drained before it is rewritten
     if (slot.in_flight) CU(cudaStreamWaitEvent(St.stream, slot.done, 0));
-    const float4 *src = displayable_frame();
     if (slot.staging.count < bytes) slot.staging.resize(bytes);
-    if (format == CLPT_READ_RGBA8) {
-        clpt_launch_pack_rgba8(src, reinterpret_cast<uchar4 *>(slot.staging.ptr), (size_t)St.width * St.height,
+    if (format == CLPT_READ_RGBA8 && accumulates_locally() && St.comm) {
+        // progressive frame across GPUs, texel read-back: every rank normalises and packs its OWN
+        // slab first, so 4 bytes per pixel cross NVLink instead of 16 (collective)
+        const size_t slab_px = (size_t)slab_rows_for(St.height) * St.width;
+        if (St.slab8.count != slab_px) St.slab8.resize(slab_px);
+        if (St.gathered8.count != slab_px * St.nranks) St.gathered8.resize(slab_px * St.nranks);
+        clpt_launch_pack_rgba8(St.slab.ptr, St.slab8.ptr, slab_px, true, St.stream);
+        NC(g_nccl.AllGather(St.slab8.ptr, St.gathered8.ptr, slab_px * 4, ncclChar, St.comm, St.stream));
+        clpt_launch_deinterleave_rgba8(St.gathered8.ptr, reinterpret_cast<uchar4 *>(slot.staging.ptr), St.width,
+                                       St.height, St.nranks, St.tile_rows, slab_rows_for(St.height), St.stream);
+        CU(cudaGetLastError());
+    } else if (format == CLPT_READ_RGBA8) {
+        const float4 *src = displayable_frame();
+        clpt_launch_pack_rgba8(src, reinterpret_cast<uchar4 *>(slot.staging.ptr), (size_t)St.width * St.height, false,
                                St.stream);
         CU(cudaGetLastError());
     } else {
+        const float4 *src = displayable_frame();
         CU(cudaMemcpyAsync(slot.staging.ptr, src, bytes, cudaMemcpyDeviceToDevice, St.stream));
     }
     CU(cudaEventRecord(slot.ready, St.stream));
@@ -629,14 +646,22 @@ void clpt_state_launch_frame(int width, int height) {
     F.flags = St.flags;
     F.log2_sample_lanes = 0;
     while (F.log2_sample_lanes < 5 && (2 << F.log2_sample_lanes) <= St.spp) F.log2_sample_lanes++;
-    // at >= 64 spp the samples of a pixel are spread over 2, 4 or 8 warps (render_kernel.cu)
+    // At >= 64 spp the samples of a pixel can be spread over 2, 4 or 8 warps (render_kernel.cu): a
+    // claim is then 1/G as long.  That only pays when a warp gets few claims per frame and the end
+    // of the frame is a visible part of it -- one GPU's share of a frame sharded over several
+    // (measured: +3..4% on an eighth of the bench frame, -1% on the whole of it).
     F.log2_warps_per_pixel = 0;
-    while (F.log2_warps_per_pixel < 3 && (64 << F.log2_warps_per_pixel) <= St.spp) F.log2_warps_per_pixel++;
-    if (const char *e = getenv("CLPT_WARPS_PER_PIXEL")) {
-        const int want = atoi(e);
+    {
+        const int rows = St.nranks > 1 ? local_rows_for(height) : height;
+        const double claims_per_warp = (double)rows * width / ((double)St.prop.multiProcessorCount * 64.0);
+        if (claims_per_warp < 150.0) {
+            while (F.log2_warps_per_pixel < 3 && (64 << F.log2_warps_per_pixel) <= St.spp) F.log2_warps_per_pixel++;
+        }
+    }
+    if (const char *e = getenv("CLPT_WARPS_PER_PIXEL")) { // measurement only
         int lg = 0;
-        while ((2 << lg) <= want && lg < 3) lg++;
-        if (F.log2_sample_lanes == 5 || lg == 0) F.log2_warps_per_pixel = lg;
+        while ((2 << lg) <= atoi(e) && lg < 3 && (64 << lg) <= St.spp) lg++;
+        F.log2_warps_per_pixel = lg;
     }
     F.seed = St.seed;
     F.sample_base = St.sample_base;
@@ -654,6 +679,7 @@ void clpt_state_launch_frame(int width, int height) {
     F.work_counter = St.work_counter.ptr;
     F.blocks_x = F.n_warp_tiles = 0;
     F.row_cost = nullptr;
+    F.row_order = nullptr;
     const bool local_only = accumulates_locally(); // progressive across GPUs: nothing crosses GPUs per frame
     const bool p2p = St.p2p && St.comm && St.nranks > 1 && !local_only;
     F.n_peer_images = p2p ? St.nranks : 0;
@@ -664,10 +690,10 @@ void clpt_state_launch_frame(int width, int height) {
         F.counters = St.counters.ptr;
     }
 
-    // Engine: 1 = every lane walks its own leaf's triangles; 2 = warp-cooperative leaves
-    // (render_kernel.cu); 0 = chosen from the tree at CLSetMeshes.
+    // Engine: 1 = the kernel compiled for 8 resident blocks per SM; 2 = for 4 (trees with fat
+    // leaves, render_kernel.cu); 0 = chosen from the tree at CLSetMeshes.
     St.last_engine = St.engine != 0 ? St.engine : St.auto_engine;
-    if (St.last_engine == 2) F.flags |= CLPT_F_COOP;
+    if (St.last_engine == 2) F.flags |= CLPT_F_FAT;
 
     // Claim direction (megakernel): decided from the previous frame's per-row cost under
     // the same image, sharding and parameters.  $CLPT_ROW_ORDER=0 turns it off.
@@ -683,18 +709,29 @@ void clpt_state_launch_frame(int width, int height) {
         const long long key[8] = { width, height, St.spp, St.mode, St.depth, St.rank, St.nranks, St.tile_rows };
         if (order_rows != St.row_count || memcmp(key, St.row_key, sizeof(key)) != 0) {
             St.claim_reverse = false;
+            St.have_row_order = false;
             St.row_count = order_rows;
             memcpy(St.row_key, key, sizeof(key));
         }
         if (order_rows > St.row_capacity) {
             if (St.host_row_cost) CU(cudaFreeHost(St.host_row_cost));
             CU(cudaMallocHost((void **)&St.host_row_cost, (size_t)order_rows * sizeof(unsigned long long)));
+            if (St.host_row_order) CU(cudaFreeHost(St.host_row_order));
+            CU(cudaMallocHost((void **)&St.host_row_order, (size_t)order_rows * sizeof(int)));
             St.row_cost.resize((size_t)order_rows);
+            St.row_order.resize((size_t)order_rows);
             St.row_capacity = order_rows;
+            St.have_row_order = false;
         }
         CU(cudaMemsetAsync(St.row_cost.ptr, 0, (size_t)order_rows * sizeof(unsigned long long), St.stream));
         F.row_cost = St.row_cost.ptr;
-        if (St.claim_reverse) F.flags |= CLPT_F_REVERSE;
+        if (St.have_row_order) { // the order (direction included) decided after the previous frame
+            CU(cudaMemcpyAsync(St.row_order.ptr, St.host_row_order, (size_t)order_rows * sizeof(int),
+                               cudaMemcpyHostToDevice, St.stream));
+            F.row_order = St.row_order.ptr;
+        } else if (St.claim_reverse) {
+            F.flags |= CLPT_F_REVERSE;
+        }
     }
     if (p2p) flag_barrier(); // every rank has finished with (reading) the previous frame
     CU(cudaEventRecord(St.ev_start, St.stream));
@@ -743,6 +780,15 @@ void clpt_state_launch_frame(int width, int height) {
     if (order_rows > 0) { // next frame starts from the end nearer to this frame's costliest rows
         double where = 0.0;
         St.claim_reverse = clpt_claim_direction(St.host_row_cost, order_rows, St.claim_reverse ? 1 : 0, &where) != 0;
+        // $CLPT_ROW_ORDER: 1 = direction only, 2 (default) = the costliest rows first, then that direction
+        const char *mode = getenv("CLPT_ROW_ORDER");
+        St.have_row_order = false;
+        if (!mode || atoi(mode) >= 2) {
+            const char *hf = getenv("CLPT_HOT_FACTOR");
+            const int n_hot = clpt_claim_order(St.host_row_cost, order_rows, St.claim_reverse ? 1 : 0,
+                                               hf ? atof(hf) : 2.0, St.host_row_order);
+            St.have_row_order = n_hot > 0;
+        }
         if (getenv("CLPT_VERBOSE") && atoi(getenv("CLPT_VERBOSE")) >= 3) {
             fprintf(stderr, "CLExecute: costliest rows at %.2f of %d, next frame claims %s\n", where, order_rows,
                     St.claim_reverse ? "bottom-up" : "top-down");
@@ -817,7 +863,7 @@ void CLTerminate(void) {
         drop(St.gpu_packed.nodes), drop(St.gpu_packed.leaves), drop(St.gpu_packed.tri), drop(St.gpu_packed.lut);
         St.gpu_tree = ClptGpuTree();
         St.gpu_packed = ClptGpuPacked();
-        St.scene_on_gpu = false;
+        St.scene_on_gpu = St.mesh_on_gpu = false;
         clpt_gpu_build_release();
     }
     St.objects.release();
@@ -827,14 +873,20 @@ void CLTerminate(void) {
     St.slab.release();
     St.gathered.release();
     St.scratch.release();
+    St.slab8.release();
+    St.gathered8.release();
     St.aov_prim.release();
     St.aov_t.release();
     St.aov_uv.release();
     St.counters.release();
     St.work_counter.release();
     St.row_cost.release();
+    St.row_order.release();
     if (St.host_row_cost) CU(cudaFreeHost(St.host_row_cost));
     St.host_row_cost = nullptr;
+    if (St.host_row_order) CU(cudaFreeHost(St.host_row_order));
+    St.host_row_order = nullptr;
+    St.have_row_order = false;
     St.row_capacity = St.row_count = 0;
     St.claim_reverse = false;
     St.dist_word.release();
@@ -923,36 +975,21 @@ void CLSetBuildParams(int max_depth, int min_split, float traversal_cost, float 
     St.build_params.empty_bonus = empty_bonus;
 }
 
-void CLBuildMeshes(const void *verts, size_t vert_bytes, const void *tris, size_t tri_bytes, const void *norms,
-                   size_t norm_bytes) {
-    require_init("CLBuildMeshes");
-    release_host_kd();
-    const size_t n_verts = vert_bytes / sizeof(Vector4), n_corners = tri_bytes / sizeof(cl_int3);
-    const size_t n_norms = norms ? norm_bytes / sizeof(Vector4) : 0;
-    if (n_verts == 0 || n_corners < 3) FATAL("CLBuildMeshes: empty mesh");
-    // the mesh crosses PCIe once; everything after it happens on the device
-    St.verts.resize(n_verts);
-    CU(cudaMemcpyAsync(St.verts.ptr, verts, n_verts * sizeof(float4), cudaMemcpyHostToDevice, St.stream));
-    St.corners.resize(n_corners);
-    CU(cudaMemcpyAsync(St.corners.ptr, tris, n_corners * sizeof(int4), cudaMemcpyHostToDevice, St.stream));
-    if (n_norms) {
-        St.norms.resize(n_norms);
-        CU(cudaMemcpyAsync(St.norms.ptr, norms, n_norms * sizeof(float4), cudaMemcpyHostToDevice, St.stream));
-    } else {
-        St.norms.release();
-    }
-    St.tri_material.release();
+namespace {
+// Build the tree of the device-resident mesh and re-lay it out, all on the device.
+void rebuild_on_device(const char *who) {
+    const size_t n_verts = St.verts.count, n_corners = St.corners.count;
     char err[256] = "";
     CU(cudaEventRecord(St.ev_build[0], St.stream));
     if (!clpt_gpu_build(St.verts.ptr, (int)n_verts, St.corners.ptr, (int)(n_corners / 3), St.build_params, St.gpu_tree,
                         St.stream, err, sizeof err)) {
-        fprintf(stderr, "CLBuildMeshes: invalid scene: %s\n", err);
+        fprintf(stderr, "%s: invalid scene: %s\n", who, err);
         exit(EXIT_FAILURE);
     }
     CU(cudaEventRecord(St.ev_build[1], St.stream));
     if (!clpt_gpu_pack(St.gpu_tree, St.verts.ptr, St.corners.ptr, (int)(n_corners / 3), St.gpu_packed, St.stream, err,
                        sizeof err)) {
-        fprintf(stderr, "CLBuildMeshes: invalid scene: %s\n", err);
+        fprintf(stderr, "%s: invalid scene: %s\n", who, err);
         exit(EXIT_FAILURE);
     }
     CU(cudaEventRecord(St.ev_build[2], St.stream));
@@ -977,6 +1014,46 @@ void CLBuildMeshes(const void *verts, size_t vert_bytes, const void *tris, size_
     if (const char *e = getenv("CLPT_ENGINE")) {
         if (atoi(e) == 1 || atoi(e) == 2) St.auto_engine = atoi(e);
     }
+}
+} // namespace
+
+void CLBuildMeshes(const void *verts, size_t vert_bytes, const void *tris, size_t tri_bytes, const void *norms,
+                   size_t norm_bytes) {
+    require_init("CLBuildMeshes");
+    release_host_kd();
+    const size_t n_verts = vert_bytes / sizeof(Vector4), n_corners = tri_bytes / sizeof(cl_int3);
+    const size_t n_norms = norms ? norm_bytes / sizeof(Vector4) : 0;
+    if (n_verts == 0 || n_corners < 3) FATAL("CLBuildMeshes: empty mesh");
+    // the mesh crosses PCIe once; everything after it happens on the device
+    St.verts.resize(n_verts);
+    CU(cudaMemcpyAsync(St.verts.ptr, verts, n_verts * sizeof(float4), cudaMemcpyHostToDevice, St.stream));
+    St.corners.resize(n_corners);
+    CU(cudaMemcpyAsync(St.corners.ptr, tris, n_corners * sizeof(int4), cudaMemcpyHostToDevice, St.stream));
+    if (n_norms) {
+        St.norms.resize(n_norms);
+        CU(cudaMemcpyAsync(St.norms.ptr, norms, n_norms * sizeof(float4), cudaMemcpyHostToDevice, St.stream));
+    } else {
+        St.norms.release();
+    }
+    St.tri_material.release();
+    St.mesh_on_gpu = true;
+    rebuild_on_device("CLBuildMeshes");
+}
+
+void CLUpdateVertices(size_t first_vertex, const void *verts, size_t vert_bytes) {
+    require_init("CLUpdateVertices");
+    if (!St.mesh_on_gpu) FATAL("CLUpdateVertices: no mesh was uploaded with CLBuildMeshes");
+    const size_t n = vert_bytes / sizeof(Vector4);
+    if (first_vertex + n > St.verts.count) FATAL("CLUpdateVertices: range past the end of the vertex array");
+    if (n) {
+        CU(cudaMemcpyAsync(St.verts.ptr + first_vertex, verts, n * sizeof(float4), cudaMemcpyHostToDevice, St.stream));
+    }
+}
+
+void CLRebuildMeshes(void) {
+    require_init("CLRebuildMeshes");
+    if (!St.mesh_on_gpu) FATAL("CLRebuildMeshes: no mesh was uploaded with CLBuildMeshes");
+    rebuild_on_device("CLRebuildMeshes");
 }
 
 void CLLastBuildMs(float *build_ms, float *pack_ms) {
@@ -1057,7 +1134,7 @@ void CLSetRenderParams(int mode, int depth, int spp, unsigned int seed, int flag
 }
 
 void CLSetEngine(int engine) {
-    if (engine < 0 || engine > 2) FATAL("CLSetEngine: 0 auto, 1 lane-per-ray leaves, 2 warp-cooperative leaves");
+    if (engine < 0 || engine > 2) FATAL("CLSetEngine: 0 auto, 1 full occupancy, 2 fat-leaf variant");
     St.engine = engine;
 }
 
@@ -1078,6 +1155,8 @@ void CLDeleteImage(void) {
     St.slab.release();
     St.gathered.release();
     St.scratch.release();
+    St.slab8.release();
+    St.gathered8.release();
     St.aov_prim.release();
     St.aov_t.release();
     St.aov_uv.release();

@@ -104,85 +104,29 @@ __device__ __forceinline__ V3 trace_sample(const ClptScene &S, const ClptFrame &
     return mk(fadd(fmul(k, col.x), str), fadd(fmul(k, col.y), str), fadd(fmul(k, col.z), str));
 }
 
-// The same sample with the warp-cooperative traversal (engine 2): every lane of the warp
-// calls this, `active` says whether it has a sample; the bounce loop is uniform across
-// the warp (lanes meet after every ray, as they do in trace_sample) so that finished
-// lanes keep helping with the fat leaves of the others.
-template <int MODE, bool COUNT>
-__device__ __forceinline__ V3 trace_sample_coop(const ClptScene &S, const ClptFrame &F, int x, int y, unsigned pixel,
-                                                unsigned sample, bool active, bool aov, Counters &cn) {
-    const unsigned FULL = 0xffffffffu;
-    V3 o = mk(0.0f, 0.0f, 0.0f), d = mk(1.0f, 0.0f, 0.0f);
-    if (active) primary_ray(F, x, y, pixel, sample, o, d);
-    int depth = F.depth;
-    if (MODE == 0) depth = depth > 0 ? 1 : 0;
-    bool alive = active && depth > 0;
-    V3 col = mk(0.0f, 0.0f, 0.0f), T = mk(1.0f, 1.0f, 1.0f); // mode C: col is the radiance sum
-    float str = 1.0f;
-    for (int seg = 0; seg < depth; seg++) {
-        if (!__any_sync(FULL, alive)) break;
-        const Hit h = closest_hit_coop<COUNT>(S, o, d, alive, F.max_leaf_visits, cn);
-        if (!alive) continue;
-        if (seg == 0 && aov) write_aov<COUNT>(S, F, h, o, d, x, y);
-        if (h.ref < 0) {
-            if (MODE == 2) col = vadd(col, T);
-            alive = false;
-            continue;
-        }
-        const V3 nrm = hit_normal<COUNT>(S, h, o, d, cn);
-        if (MODE == 2) {
-            float al[3] = { 0.5f, 0.5f, 0.5f }, em[3] = { 0.0f, 0.0f, 0.0f };
-            int kind = 0;
-            if (S.n_materials > 0) {
-                int m = S.tri_material ? __ldg(S.tri_material + __float_as_int(__ldg(&S.tri[3 * (size_t)h.ref].w))) : 0;
-                if (m < 0 || m >= S.n_materials) m = 0;
-                const ClptMaterial *mp = S.materials + m;
-                al[0] = mp->albedo[0]; al[1] = mp->albedo[1]; al[2] = mp->albedo[2];
-                em[0] = mp->emission[0]; em[1] = mp->emission[1]; em[2] = mp->emission[2];
-                kind = mp->kind;
-            }
-            col = vadd(col, mk(fmul(T.x, em[0]), fmul(T.y, em[1]), fmul(T.z, em[2])));
-            T = mk(fmul(T.x, al[0]), fmul(T.y, al[1]), fmul(T.z, al[2]));
-            const V3 hp = vadd(o, vscale(d, h.t));
-            const V3 nd = kind == 1 ? vnormalize(vsub(d, vscale(nrm, fmul(2.0f, vdot(d, nrm)))))
-                                    : cosine_dir(nrm, pixel, sample, (unsigned)seg, F.seed);
-            o = vadd(hp, vscale(nd, 0.0001f));
-            d = nd;
-            continue;
-        }
-        const V3 nc = mk(fdiv(fadd(nrm.x, 1.0f), 2.0f), fdiv(fadd(nrm.y, 1.0f), 2.0f),
-                         fdiv(fadd(nrm.z, 1.0f), 2.0f));
-        if (MODE == 0) { // the `return` at :396
-            col = nc;
-            str = 0.0f; // marks "colour is final"
-            alive = false;
-            continue;
-        }
-        V3 no = vadd(o, vscale(d, h.t));
-        const V3 nd = vnormalize(vsub(d, vscale(nrm, fmul(2.0f, vdot(d, nrm)))));
-        no = vadd(no, vscale(nd, 0.0001f));
-        col = vadd(vscale(col, fsub(1.0f, str)), vscale(nc, str));
-        str = fmul(str, 0.2f);
-        o = no;
-        d = nd;
-    }
-    if (MODE == 2) return col;
-    if (MODE == 0 && str == 0.0f) return col;
-    const float k = fsub(1.0f, str); // :421
-    return mk(fadd(fmul(k, col.x), str), fadd(fmul(k, col.y), str), fadd(fmul(k, col.z), str));
-}
-
-// Barrier among the G warps that share a pixel (named barrier 1 + group; __syncwarp for G = 1).
+// Barrier among the G warps that share a pixel (__syncwarp for G = 1).  Named barriers 1-4,
+// one per group, with IMMEDIATE ids: a barrier id held in a register makes ptxas reserve all
+// 16 barriers for the block, and barriers are an occupancy limit like registers
+// (launch__occupancy_limit_barriers) -- 16 per block allowed 4 resident blocks instead of 8
+// and cost 40% of the frame rate (profiles/r02_experiments.json).
 __device__ __forceinline__ void group_sync(int log2_g, int group) {
     if (log2_g == 0) {
         __syncwarp();
-    } else {
-        asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(32 << log2_g) : "memory");
+        return;
+    }
+    const int threads = 32 << log2_g;
+    switch (group) {
+    case 0: asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory"); break;
+    case 1: asm volatile("bar.sync 2, %0;" ::"r"(threads) : "memory"); break;
+    case 2: asm volatile("bar.sync 3, %0;" ::"r"(threads) : "memory"); break;
+    default: asm volatile("bar.sync 4, %0;" ::"r"(threads) : "memory"); break;
     }
 }
 
-template <int MODE, bool COUNT, bool COOP>
-__global__ void __launch_bounds__(256, COOP ? CLPT_COOP_MIN_BLOCKS : CLPT_MIN_BLOCKS)
+// VARIANT 0: compiled for 8 resident blocks per SM (engine 1).  1: the same code for
+// CLPT_FAT_MIN_BLOCKS (engine 2, trees with fat leaves).
+template <int MODE, bool COUNT, int VARIANT>
+__global__ void __launch_bounds__(256, VARIANT == 1 ? CLPT_FAT_MIN_BLOCKS : CLPT_MIN_BLOCKS)
 render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptFrame F) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int log2_s = F.log2_sample_lanes, s_lanes = 1 << log2_s;
@@ -243,7 +187,9 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
         if (t >= n_tiles) break;
         if (F.flags & CLPT_F_REVERSE) t = n_tiles - 1u - t;
         const unsigned w = t & 7u, b = t >> 3;
-        const int bx = (int)(b % bx_count), by = (int)(b / bx_count);
+        const int bx = (int)(b % bx_count);
+        int by = (int)(b / bx_count);
+        if (F.row_order) by = __ldg(F.row_order + by);
         if (lane == 0 && member == 0) tile_row[warp] = (unsigned)by;
         const int x = (bx * 4 + (int)(w & 3u)) * tw + (pslot & (tw - 1));
         const int ly = (by * 2 + (int)(w >> 2)) * th + pslot / tw; // row within this rank's slab
@@ -262,10 +208,8 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
                 none.t = 0.0f;
                 write_aov<COUNT>(S, F, none, mk(0.0f, 0.0f, 0.0f), mk(0.0f, 0.0f, 0.0f), x, y);
             }
-            if (COOP) {
-                colour = trace_sample_coop<MODE, COUNT>(S, F, x, y, pixel, F.sample_base + (unsigned)s,
-                                                        valid && s < spp, s == 0 && F.aov_prim != nullptr, cn);
-            } else if (valid && s < spp) {
+            const int in_round = min(round_samples, spp - base);
+            if (valid && s < spp) {
                 colour = trace_sample<MODE, COUNT>(S, F, x, y, pixel, F.sample_base + (unsigned)s,
                                                    s == 0 && F.aov_prim != nullptr, cn);
             }
@@ -273,7 +217,6 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
             my_stage[1 * row_len + my_col] = colour.y;
             my_stage[2 * row_len + my_col] = colour.z;
             group_sync(log2_g, group);
-            const int in_round = min(round_samples, spp - base);
             if (member == 0) {
                 if (per_channel) {
                     if (sslot < 3) {
@@ -313,8 +256,9 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
     }
 }
 
-// Gathered slabs [rank][slab_rows][width] -> image rows.
-__global__ void deinterleave_kernel(const float4 *__restrict__ gathered, float4 *__restrict__ image,
+// Gathered slabs [rank][slab_rows][width] -> image rows (float4 pixels or RGBA8 texels).
+template <typename PX>
+__global__ void deinterleave_kernel(const PX *__restrict__ gathered, PX *__restrict__ image,
                                     int width, int height, int nranks, int tile_rows,
                                     int slab_rows) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -346,10 +290,19 @@ __global__ void normalise_kernel(const float4 *__restrict__ src, float4 *__restr
 // Displayable float4 frame -> RGBA8 UNORM texels, the format of the reference's render
 // target (src/GLHandler.c:177-185): what write_imagef does to a CL_UNORM_INT8 image,
 // clamp to [0,1], scale by 255, round to nearest even.
-__global__ void pack_rgba8_kernel(const float4 *__restrict__ src, uchar4 *__restrict__ dst, size_t n) {
+// normalise != 0: src holds running sums with the sample count in .w (progressive frames).
+__global__ void pack_rgba8_kernel(const float4 *__restrict__ src, uchar4 *__restrict__ dst, size_t n, int normalise) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float4 c = src[i];
+    float4 c = src[i];
+    if (normalise) {
+        if (c.w > 0.0f) {
+            const float k = __fdiv_rn(1.0f, c.w);
+            c = make_float4(__fmul_rn(c.x, k), __fmul_rn(c.y, k), __fmul_rn(c.z, k), 1.0f);
+        } else {
+            c = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+    }
     dst[i] = make_uchar4((unsigned char)clpt_to_unorm8(c.x), (unsigned char)clpt_to_unorm8(c.y),
                          (unsigned char)clpt_to_unorm8(c.z), (unsigned char)clpt_to_unorm8(c.w));
 }
@@ -373,13 +326,13 @@ __global__ void flag_barrier_kernel(const __grid_constant__ ClptFlagPeers peers,
 
 template <int MODE>
 void launch_mode(const ClptScene &scene, const ClptFrame &frame, unsigned grid, cudaStream_t stream) {
-    const bool coop = (frame.flags & CLPT_F_COOP) != 0;
+    const bool fat = (frame.flags & CLPT_F_FAT) != 0;
     if (frame.flags & CLPT_F_COUNTERS) {
-        if (coop) render_kernel<MODE, true, true><<<grid, 256, 0, stream>>>(scene, frame);
-        else render_kernel<MODE, true, false><<<grid, 256, 0, stream>>>(scene, frame);
+        if (fat) render_kernel<MODE, true, 1><<<grid, 256, 0, stream>>>(scene, frame);
+        else render_kernel<MODE, true, 0><<<grid, 256, 0, stream>>>(scene, frame);
     } else {
-        if (coop) render_kernel<MODE, false, true><<<grid, 256, 0, stream>>>(scene, frame);
-        else render_kernel<MODE, false, false><<<grid, 256, 0, stream>>>(scene, frame);
+        if (fat) render_kernel<MODE, false, 1><<<grid, 256, 0, stream>>>(scene, frame);
+        else render_kernel<MODE, false, 0><<<grid, 256, 0, stream>>>(scene, frame);
     }
 }
 
@@ -403,7 +356,7 @@ void clpt_launch_render(const ClptScene &scene, const ClptFrame &frame_in, int s
     frame.blocks_x = (int)bx;
     frame.n_warp_tiles = (int)(bx * by * 8u);
     // persistent grid: enough blocks to fill every SM, never more than there are tiles
-    unsigned grid = (unsigned)sm_count * ((frame.flags & CLPT_F_COOP) ? CLPT_COOP_MIN_BLOCKS : CLPT_MIN_BLOCKS);
+    unsigned grid = (unsigned)sm_count * ((frame.flags & CLPT_F_FAT) ? CLPT_FAT_MIN_BLOCKS : CLPT_MIN_BLOCKS);
     if (grid > bx * by) grid = bx * by;
     cudaMemsetAsync(frame.work_counter, 0, sizeof(unsigned), stream);
     switch (frame.mode) {
@@ -417,8 +370,16 @@ void clpt_launch_deinterleave(const float4 *gathered, float4 *image, int width, 
                               int nranks, int tile_rows, int slab_rows, cudaStream_t stream) {
     const size_t n = (size_t)width * height;
     if (n == 0) return;
-    deinterleave_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(gathered, image, width, height,
-                                                                         nranks, tile_rows, slab_rows);
+    deinterleave_kernel<float4><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(gathered, image, width, height,
+                                                                                 nranks, tile_rows, slab_rows);
+}
+
+void clpt_launch_deinterleave_rgba8(const uchar4 *gathered, uchar4 *image, int width, int height, int nranks,
+                                    int tile_rows, int slab_rows, cudaStream_t stream) {
+    const size_t n = (size_t)width * height;
+    if (n == 0) return;
+    deinterleave_kernel<uchar4><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(gathered, image, width, height,
+                                                                                 nranks, tile_rows, slab_rows);
 }
 
 void clpt_launch_fill(float4 *dst, size_t n, float value, cudaStream_t stream) {
@@ -436,11 +397,11 @@ void clpt_launch_flag_barrier(const ClptFlagPeers &peers, int rank, int nranks, 
     flag_barrier_kernel<<<1, 32, 0, stream>>>(peers, rank, nranks, epoch);
 }
 
-void clpt_launch_pack_rgba8(const float4 *src, uchar4 *dst, size_t n, cudaStream_t stream) {
+void clpt_launch_pack_rgba8(const float4 *src, uchar4 *dst, size_t n, bool normalise, cudaStream_t stream) {
     if (n == 0) return;
-    pack_rgba8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, dst, n);
+    pack_rgba8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, dst, n, normalise ? 1 : 0);
 }
 
 const void *clpt_render_kernel_symbol(void) {
-    return reinterpret_cast<const void *>(&render_kernel<0, false, false>);
+    return reinterpret_cast<const void *>(&render_kernel<0, false, 0>);
 }

@@ -124,6 +124,12 @@ void CLBuildMeshes(const void *verts, size_t vert_bytes, const void *tris, size_
                    const void *norms, size_t norm_bytes);
 void CLSetBuildParams(int max_depth, int min_split, float traversal_cost, float intersect_cost,
                       float empty_bonus);
+/* Animated scenes (BASELINE config 5: per-frame object transform + kd-tree re-upload):
+ * overwrite a range of the uploaded vertex array in place -- only the vertices that
+ * moved cross PCIe -- and rebuild tree and layout on the device from the resident
+ * mesh.  CLBuildMeshes == upload + CLRebuildMeshes. */
+void CLUpdateVertices(size_t first_vertex, const void *verts, size_t vert_bytes);
+void CLRebuildMeshes(void);
 void CLLastBuildMs(float *build_ms, float *pack_ms); /* device time of the last CLBuildMeshes */
 void CLBuildStats(int *nodes, int *tri_refs, int *levels);
 /* The tree CLBuildMeshes built, as a regular `kd` (fresh host lists the caller owns and
@@ -140,13 +146,14 @@ void CLSetMaterials(const CLMaterial *materials, size_t material_bytes,
  * samples per pixel per frame, RNG seed, CLPT_FLAG_* */
 void CLSetRenderParams(int mode, int depth, int spp, unsigned int seed, int flags);
 void CLSetMaxLeafVisits(int cap);          /* rope-hop cap per ray; default 4096 */
-/* Execution engine: 1 = every lane walks the triangle run of its own leaf; 2 = the
- * lanes of a warp stay in one traversal loop and share the triangle runs of fat
- * leaves (>= 8 triangles: 32 triangles per step, ordered reduction) -- made for
- * trees from the reference's own builder, whose DEPTH 15 cap (src/kd_tree.c:8-9)
- * leaves ~56 triangles per leaf at 1M triangles; 0 = automatic: chosen per tree at
- * CLSetMeshes (2 when most triangle slots sit in fat leaves).  Both produce the same
- * bits; the choice is about speed only. */
+/* Execution engine: 1 = the render kernel compiled for 8 resident blocks per SM (32
+ * registers), the fastest on deep trees where latency hiding decides; 2 = the same
+ * code compiled for 4 (64 registers, no spills) -- made for trees from the
+ * reference's own builder, whose DEPTH 15 cap (src/kd_tree.c:8-9) leaves ~56
+ * triangles per leaf at 1M triangles: their frames end with a few warps walking
+ * thousands of triangles, and a warp runs faster when fewer are resident;
+ * 0 = automatic: chosen per tree at CLSetMeshes (2 when most triangle slots sit in
+ * leaves of >= 8 triangles).  Both produce the same bits. */
 void CLSetEngine(int engine);
 int CLLastEngine(void);                    /* engine the last CLExecute used: 1 or 2 */
 void CLCreateImageHeadless(int width, int height); /* float4 target, zeroed */

@@ -16,3 +16,5 @@ CLPT_WARPS_PER_PIXEL=1 python bench.py --no-cpu-baseline --no-parity-check > gpu
 CLPT_WARPS_PER_PIXEL=4 python bench.py --no-cpu-baseline --no-parity-check > gpurun_out/r02_bench_g4.json 2> gpurun_out/r02_bench_g4.err
 python profiles/experiments/shard_kernel_times.py > gpurun_out/r02_shard_g2.txt 2>&1
 CLPT_WARPS_PER_PIXEL=1 python profiles/experiments/shard_kernel_times.py > gpurun_out/r02_shard_g1.txt 2>&1
+CLPT_REGROUP=0 python bench.py --no-cpu-baseline --no-parity-check > gpurun_out/r02_bench_noregroup.json 2> gpurun_out/r02_bench_noregroup.err
+CLPT_REGROUP=0 python profiles/experiments/shard_kernel_times.py > gpurun_out/r02_shard_g2_noregroup.txt 2>&1

@@ -17,17 +17,17 @@ r = cl.Renderer(device=0)
 r.set_meshes(scene); r.set_camera_matrix(cam)
 r.set_params(mode=1, depth=5, spp=64, seed=0, flags=cl.FLAG_JITTER)
 out = {}
-for nranks in (1, 4, 8):
+for nranks in (1, 8):
     for rank in sorted({0, nranks - 1}):
         L.CLSetTileShard(rank, nranks, 8)
         r.create_image(w, h)
-        for rev in (0, 1):  # 1 = cost-ordered claims
+        for rev in (0, 1, 2):  # 0 = screen order, 1 = claim direction, 2 = costliest rows first + direction
             os.environ["CLPT_ROW_ORDER"] = str(rev)
             ms = []
-            for k in range(5):
+            for k in range(6):
                 L.CLFlushL2()
                 r.execute()
-                if k >= 2: ms.append(L.CLLastKernelMs())
+                if k >= 3: ms.append(L.CLLastKernelMs())
             out[f"shard {rank}/{nranks} ordered {rev}"] = round(float(np.mean(ms)), 4)
             print(f"shard {rank}/{nranks} ordered {rev}: {np.mean(ms):.4f} ms  (x{nranks} = {np.mean(ms)*nranks:.2f})", flush=True)
 json.dump(out, open("gpurun_out/row_order_exp.json", "w"), indent=1)

@@ -139,6 +139,23 @@ def test_device_build_is_deterministic(clpt, renderer):
     assert a.nodes.tobytes() == b.nodes.tobytes() and a.tri_indices.tobytes() == b.tri_indices.tobytes()
 
 
+def test_update_vertices_and_rebuild(clpt, renderer):
+    """Animated scenes: moving some vertices in place and rebuilding from the device-resident mesh
+    gives the tree a fresh upload of the moved mesh gives."""
+    v, c, n = _mesh("hf60")
+    renderer.build_meshes(v, c, n)
+    moved = v.copy()
+    moved[100:400, 1] += np.float32(0.07)
+    renderer.update_vertices(100, moved[100:400])
+    renderer.rebuild_meshes()
+    a = renderer.download_kd()
+    renderer.build_meshes(moved, c, n)
+    b = renderer.download_kd()
+    assert a.nodes.tobytes() == b.nodes.tobytes() and a.tri_indices.tobytes() == b.tri_indices.tobytes()
+    assert a.verts.tobytes() == b.verts.tobytes()
+    _check_tree(a, exhaustive=False)
+
+
 def test_device_build_quality_and_speed(clpt, renderer):
     """On a 100k-triangle mesh the device tree is in the class of the host SAH tree (within 2x
     of its triangle references) and is built in milliseconds, not the host's hundreds."""

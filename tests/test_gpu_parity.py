@@ -106,11 +106,10 @@ COOP_CASES = [
 
 
 @pytest.mark.parametrize("name,tree,camera,w,h,mode,depth,spp,flags", COOP_CASES)
-def test_cooperative_engine_bit_exact(clpt, oracle, renderer, scene_cache, name, tree, camera, w, h, mode, depth, spp,
+def test_fat_leaf_engine_bit_exact(clpt, oracle, renderer, scene_cache, name, tree, camera, w, h, mode, depth, spp,
                                       flags):
-    """Engine 2 (the lanes of a warp share the triangle runs of fat leaves; ordered
-    reduction for the later-triangle-wins tie rule, src/kernel.cl:344) produces the same
-    bits as the oracle and as engine 1, work counters included."""
+    """Engine 2 (the kernel compiled for fewer resident blocks, chosen for trees with fat
+    leaves) produces the same bits as the oracle and as engine 1, work counters included."""
     from clpathtracer_b200 import scenes
 
     if isinstance(tree, bool):
@@ -144,13 +143,13 @@ def test_cooperative_engine_bit_exact(clpt, oracle, renderer, scene_cache, name,
     _assert_bit_equal(uv, ref["uv"], "uv")
     _assert_bit_equal(img, ref["rgba"], "rgba")
     _assert_bit_equal(plain, ref["rgba"], "rgba (uninstrumented kernel)")
-    _assert_bit_equal(img, lane, "cooperative vs lane-per-ray")
+    _assert_bit_equal(img, lane, "engine 2 vs engine 1")
     assert got_counters == ref["counters"]
 
 
 def test_engine_is_chosen_per_tree(clpt, renderer, scene_cache):
-    """Automatic engine: cooperative for trees whose triangles sit in fat leaves (the
-    reference builder at 100k triangles), lane-per-ray for SAH trees."""
+    """Automatic engine: the fat-leaf variant for trees whose triangles sit in fat leaves (the
+    reference builder at 100k triangles), the full-occupancy kernel for SAH trees."""
     L = clpt.lib()
     L.CLSetEngine(0)
     cam = _cam(clpt, "canonical", 48)
@@ -209,23 +208,41 @@ def test_jittered_multisample(clpt, oracle, renderer, scene_cache):
     assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("spp,engine", [(64, 1), (130, 1), (300, 1), (64, 2), (33, 1)])
-def test_samples_spread_over_warps(clpt, oracle, renderer, scene_cache, spp, engine):
-    """At >= 64 spp the samples of a pixel are traced by 2, 4 or 8 warps side by side and summed
-    by the first of them in ascending sample order: the image does not depend on the spread
-    (64 -> 2 warps, one round; 130 -> 4 warps, a full round and one of 2 samples; 300 -> 8
-    warps; 33 -> one warp, two rounds)."""
-    scene, _ = scene_cache("hf22n")
+@pytest.mark.parametrize("spp,engine,mode,warps", [(64, 1, 1, 0), (130, 1, 1, 0), (300, 1, 1, 0), (64, 2, 1, 0),
+                                                   (33, 1, 1, 0), (64, 1, 1, 1), (130, 1, 2, 0), (64, 1, 0, 0),
+                                                   (300, 1, 2, 2)])
+def test_samples_spread_over_warps(clpt, oracle, renderer, scene_cache, monkeypatch, spp, engine, mode, warps):
+    """At >= 64 spp (small frames / sharded frames) the samples of a pixel are traced by 2, 4 or 8
+    warps side by side and summed by the first of them in ascending sample order: the image does
+    not depend on the spread (64 -> 2 warps, one round; 130 -> 4 warps, a full round and one of
+    2 samples; 300 -> 8 warps; 33 -> one warp, two rounds; warps != 0 forces a spread)."""
+    scene, extra = scene_cache("cornell" if mode == 2 else "hf22n")
     w, h = 61, 37
-    cam = _cam(clpt, "canonical", h)
-    kw = dict(mode=1, depth=4, spp=spp, seed=3, flags=clpt.FLAG_JITTER)
+    cam = _cam(clpt, "cornell" if mode == 2 else "canonical", h)
+    kw = dict(mode=mode, depth=4, spp=spp, seed=3, flags=clpt.FLAG_JITTER)
+    okw = {}
+    if warps:
+        monkeypatch.setenv("CLPT_WARPS_PER_PIXEL", str(warps))
     L = clpt.lib()
     try:
         L.CLSetEngine(engine)
-        img, prim, t, uv = _render_gpu(renderer, scene, cam, w, h, **kw)
+        if mode == 2:
+            from clpathtracer_b200 import scenes
+
+            renderer.set_meshes(scene)
+            renderer.set_materials(scenes.CORNELL_MATERIALS, extra["tri_material"])
+            okw = dict(materials=scenes.CORNELL_MATERIALS, tri_material=extra["tri_material"])
+            renderer.set_camera_matrix(cam)
+            renderer.set_params(**kw)
+            renderer.create_image(w, h, aov=True)
+            renderer.execute()
+            img = renderer.read_image()
+            prim, t, uv = renderer.read_aov()
+        else:
+            img, prim, t, uv = _render_gpu(renderer, scene, cam, w, h, **kw)
     finally:
         L.CLSetEngine(0)
-    ref = oracle.render(scene, cam, w, h, **kw)
+    ref = oracle.render(scene, cam, w, h, **kw, **okw)
     assert np.array_equal(prim, ref["prim"])
     _assert_bit_equal(img, ref["rgba"], f"{spp} spp")
 
