@@ -637,14 +637,25 @@ def main():
         my_bytes = algorithmic_bytes(counters, len(cl_rows(a, rank, world)) * a.width)
         kernel_ms = float(np.mean(kern_ms))
         achieved = my_bytes / (kernel_ms * 1e-3) / 1e9
-        traffic, ncu = None, None
-        tp = ROOT / "profiles" / "traffic.json"
-        if tp.exists() and a.config == "c3":  # the capture is of this workload
+        # What binds: one ncu --set full capture per workload (profiles/binding.json, made by
+        # profiles/summarise_ncu.py from the .ncu-rep of the same command at N = 1).  DRAM traffic and
+        # unit utilisations are properties of that captured launch; at N > 1 a launch covers 1/N of
+        # the frame, so they are attached for reference and labelled, not scaled.
+        traffic, binding = None, None
+        bp = ROOT / "profiles" / "binding.json"
+        key = a.config if a.mode == "mirror" and not a.no_jitter else ("modeA_ref" if a.builder == "ref" else "modeA_sah")
+        if bp.exists():
             try:
-                ncu = json.loads(tp.read_text())
-                traffic = ncu.get("dram_bytes_per_launch")
+                binding = json.loads(bp.read_text()).get(key)
             except Exception:
-                traffic, ncu = None, None
+                binding = None
+        if binding is not None:
+            binding = dict(binding, captured_at_n_gpus=1,
+                           note="lane_issue_efficiency = issue-slot utilisation x active threads per warp instruction / 32: "
+                                "the share of the SMs' lane-issue capacity that does work; the busiest unit is the one "
+                                "that binds this kernel, not HBM")
+            if world == 1:
+                traffic = binding.get("dram_bytes_per_launch")
         out = {
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
@@ -665,10 +676,11 @@ def main():
                          "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
                          "kernel": "render_kernel<%d,false,%d>" % (mode, L.CLLastEngine() - 1),
                          "kernel_ms": round(kernel_ms, 4),
-                         "note": "DRAM traffic is ~1% of the algorithmic bytes: the working set is served by L1/L2, "
-                                 "so the HBM fraction can exceed 1; the binding limits are issue slots and SIMT "
-                                 "divergence (see ncu)",
-                         "ncu": ncu,
+                         "note": "formal bound per SURVEY.md section 8d: algorithmic bytes / kernel time against the measured "
+                                 "HBM copy bandwidth.  It does NOT bind (the scene is served by L1/L2; measured DRAM "
+                                 "traffic is in `traffic`), so this fraction can exceed 1 and earns nothing by itself; "
+                                 "`binding` names the unit that does bind and its utilisation",
+                         "binding": binding,
                          "algorithmic_bytes_per_launch": my_bytes,
                          "bytes_per_ray": round(my_bytes / max(counters["rays"], 1), 1)},
             "rays_per_frame": rays_per_frame,

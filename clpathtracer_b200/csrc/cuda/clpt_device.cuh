@@ -88,9 +88,6 @@ struct ClptFrame {
     // row_cost[its block row] (null = not recorded); CLExecute looks at where one frame's
     // cost sits and points the next frame's claims so that they END at the cheap side.
     unsigned long long *row_cost;
-    // Claim order: when set, the k-th row of blocks claimed is screen row row_order[k] (the
-    // previous frame's costliest rows first, csrc/host/frame_sched.c) and CLPT_F_REVERSE is unused.
-    const int *row_order;
     int blocks_x, n_warp_tiles;   // filled in by clpt_launch_render
 };
 

@@ -174,9 +174,7 @@ struct {
     int row_count = 0;         // rows the current direction was measured on
     long long row_key[8] = {}; // ... and under which image / sharding / parameters
     bool claim_reverse = false;
-    DevBuf<int> row_order;        // claim order of the next frame (hot rows first), see frame_sched.c
-    int *host_row_order = nullptr; // pinned
-    bool have_row_order = false;
+
     unsigned long long frames_rendered = 0;
     unsigned long long host_counters[6] = { 0 };
     float last_kernel_ms = 0;
@@ -679,7 +677,6 @@ void clpt_state_launch_frame(int width, int height) {
     F.work_counter = St.work_counter.ptr;
     F.blocks_x = F.n_warp_tiles = 0;
     F.row_cost = nullptr;
-    F.row_order = nullptr;
     const bool local_only = accumulates_locally(); // progressive across GPUs: nothing crosses GPUs per frame
     const bool p2p = St.p2p && St.comm && St.nranks > 1 && !local_only;
     F.n_peer_images = p2p ? St.nranks : 0;
@@ -709,29 +706,18 @@ void clpt_state_launch_frame(int width, int height) {
         const long long key[8] = { width, height, St.spp, St.mode, St.depth, St.rank, St.nranks, St.tile_rows };
         if (order_rows != St.row_count || memcmp(key, St.row_key, sizeof(key)) != 0) {
             St.claim_reverse = false;
-            St.have_row_order = false;
             St.row_count = order_rows;
             memcpy(St.row_key, key, sizeof(key));
         }
         if (order_rows > St.row_capacity) {
             if (St.host_row_cost) CU(cudaFreeHost(St.host_row_cost));
             CU(cudaMallocHost((void **)&St.host_row_cost, (size_t)order_rows * sizeof(unsigned long long)));
-            if (St.host_row_order) CU(cudaFreeHost(St.host_row_order));
-            CU(cudaMallocHost((void **)&St.host_row_order, (size_t)order_rows * sizeof(int)));
             St.row_cost.resize((size_t)order_rows);
-            St.row_order.resize((size_t)order_rows);
             St.row_capacity = order_rows;
-            St.have_row_order = false;
         }
         CU(cudaMemsetAsync(St.row_cost.ptr, 0, (size_t)order_rows * sizeof(unsigned long long), St.stream));
         F.row_cost = St.row_cost.ptr;
-        if (St.have_row_order) { // the order (direction included) decided after the previous frame
-            CU(cudaMemcpyAsync(St.row_order.ptr, St.host_row_order, (size_t)order_rows * sizeof(int),
-                               cudaMemcpyHostToDevice, St.stream));
-            F.row_order = St.row_order.ptr;
-        } else if (St.claim_reverse) {
-            F.flags |= CLPT_F_REVERSE;
-        }
+        if (St.claim_reverse) F.flags |= CLPT_F_REVERSE;
     }
     if (p2p) flag_barrier(); // every rank has finished with (reading) the previous frame
     CU(cudaEventRecord(St.ev_start, St.stream));
@@ -780,15 +766,6 @@ void clpt_state_launch_frame(int width, int height) {
     if (order_rows > 0) { // next frame starts from the end nearer to this frame's costliest rows
         double where = 0.0;
         St.claim_reverse = clpt_claim_direction(St.host_row_cost, order_rows, St.claim_reverse ? 1 : 0, &where) != 0;
-        // $CLPT_ROW_ORDER: 1 = direction only, 2 (default) = the costliest rows first, then that direction
-        const char *mode = getenv("CLPT_ROW_ORDER");
-        St.have_row_order = false;
-        if (!mode || atoi(mode) >= 2) {
-            const char *hf = getenv("CLPT_HOT_FACTOR");
-            const int n_hot = clpt_claim_order(St.host_row_cost, order_rows, St.claim_reverse ? 1 : 0,
-                                               hf ? atof(hf) : 2.0, St.host_row_order);
-            St.have_row_order = n_hot > 0;
-        }
         if (getenv("CLPT_VERBOSE") && atoi(getenv("CLPT_VERBOSE")) >= 3) {
             fprintf(stderr, "CLExecute: costliest rows at %.2f of %d, next frame claims %s\n", where, order_rows,
                     St.claim_reverse ? "bottom-up" : "top-down");
@@ -881,12 +858,8 @@ void CLTerminate(void) {
     St.counters.release();
     St.work_counter.release();
     St.row_cost.release();
-    St.row_order.release();
     if (St.host_row_cost) CU(cudaFreeHost(St.host_row_cost));
     St.host_row_cost = nullptr;
-    if (St.host_row_order) CU(cudaFreeHost(St.host_row_order));
-    St.host_row_order = nullptr;
-    St.have_row_order = false;
     St.row_capacity = St.row_count = 0;
     St.claim_reverse = false;
     St.dist_word.release();

@@ -187,9 +187,7 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
         if (t >= n_tiles) break;
         if (F.flags & CLPT_F_REVERSE) t = n_tiles - 1u - t;
         const unsigned w = t & 7u, b = t >> 3;
-        const int bx = (int)(b % bx_count);
-        int by = (int)(b / bx_count);
-        if (F.row_order) by = __ldg(F.row_order + by);
+        const int bx = (int)(b % bx_count), by = (int)(b / bx_count);
         if (lane == 0 && member == 0) tile_row[warp] = (unsigned)by;
         const int x = (bx * 4 + (int)(w & 3u)) * tw + (pslot & (tw - 1));
         const int ly = (by * 2 + (int)(w >> 2)) * th + pslot / tw; // row within this rank's slab

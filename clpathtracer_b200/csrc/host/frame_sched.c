@@ -56,69 +56,3 @@ clpt_claim_direction(const unsigned long long *row_cost, int rows, int current, 
     }
     return current;
 }
-
-/* Claim ORDER: the rows of the costliest band first, then the rest.
- *
- * The direction rule above makes a frame END on its cheap side.  On short frames that is not
- * enough: the rows under the horizon hold rays that graze the whole terrain (thousands of
- * triangle tests each on a shallow tree), one such tile runs for a large part of the frame,
- * and when it is claimed half-way through, the frame ends with a handful of warps finishing
- * their tiles on an otherwise idle GPU.  Claimed FIRST, the same tiles run beside all the
- * cheap ones.  "Hot" rows are those whose cost (3-row mean) exceeds `hot_factor` times the
- * mean row cost, at most a quarter of the rows; they keep their screen order (neighbouring
- * claims stay neighbours in the tree -- sorting all rows by cost was measured in round 1 and
- * loses more in locality than it wins), and so do the others, which follow in the given
- * direction.
- *
- *   order     out: order[k] = screen row claimed k-th (a permutation of 0..rows-1)
- *   reverse   direction of the rows that are not hot (clpt_claim_direction)
- * Returns the number of hot rows (0: plain order in the given direction).
- */
-int
-clpt_claim_order(const unsigned long long *row_cost, int rows, int reverse, double hot_factor, int *order) {
-    int n_hot = 0;
-    if (rows <= 0) {
-        return 0;
-    }
-    unsigned char hot[4096];
-    const int can_mark = rows >= 16 && rows <= (int)sizeof(hot);
-    if (can_mark) {
-        double total = 0.0;
-        for (int i = 0; i < rows; i++) {
-            total += (double)row_cost[i];
-        }
-        const double mean = total / rows;
-        int budget = rows / 4;
-        for (int i = 0; i < rows; i++) {
-            const double a = (double)row_cost[i > 0 ? i - 1 : i], b = (double)row_cost[i],
-                         c = (double)row_cost[i + 1 < rows ? i + 1 : i];
-            hot[i] = total > 0.0 && (a + b + c) / 3.0 > hot_factor * mean;
-            n_hot += hot[i];
-        }
-        while (n_hot > budget) { /* keep the costliest: drop the cheapest marked row */
-            int drop = -1;
-            for (int i = 0; i < rows; i++) {
-                if (hot[i] && (drop < 0 || row_cost[i] < row_cost[drop])) {
-                    drop = i;
-                }
-            }
-            hot[drop] = 0;
-            n_hot--;
-        }
-    }
-    int k = 0;
-    if (can_mark) {
-        for (int i = 0; i < rows; i++) {
-            if (hot[i]) {
-                order[k++] = i;
-            }
-        }
-    }
-    for (int j = 0; j < rows; j++) {
-        const int i = reverse ? rows - 1 - j : j;
-        if (!can_mark || !hot[i]) {
-            order[k++] = i;
-        }
-    }
-    return n_hot;
-}

@@ -7,7 +7,6 @@ extern "C" {
 #endif
 
 int clpt_claim_direction(const unsigned long long *row_cost, int rows, int current, double *where);
-int clpt_claim_order(const unsigned long long *row_cost, int rows, int reverse, double hot_factor, int *order);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,7 @@ for nranks in (1, 8):
     for rank in sorted({0, nranks - 1}):
         L.CLSetTileShard(rank, nranks, 8)
         r.create_image(w, h)
-        for rev in (0, 1, 2):  # 0 = screen order, 1 = claim direction, 2 = costliest rows first + direction
+        for rev in (0, 1):  # 0 = screen order, 1 = claim direction
             os.environ["CLPT_ROW_ORDER"] = str(rev)
             ms = []
             for k in range(6):

@@ -50,3 +50,4 @@ def test_hysteresis_and_degenerate_inputs(clpt):
     flat = rng.integers(900, 1100, size=rows).astype(np.uint64)             # noise only: wherever the
     d0 = _direction(clpt, flat, 0)[0]                                       # maximum falls, the answer
     assert _direction(clpt, flat, d0)[0] == d0                              # is stable once taken
+

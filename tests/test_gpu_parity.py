@@ -510,6 +510,28 @@ def test_full_size_properties_1m(clpt, oracle, renderer):
     assert np.array_equal(a_img[prim < 0], np.ones_like(a_img[prim < 0]))
 
 
+def test_moving_camera_keeps_parity_while_the_claim_direction_adapts(clpt, oracle, renderer, scene_cache):
+    """The claim direction (decided from the PREVIOUS frame's per-row cost, csrc/host/frame_sched.c)
+    is a scheduling decision only: with a camera that tilts from looking down to looking at the
+    horizon and back -- the costly band moves across the frame and flips sides -- every frame
+    still equals the oracle's."""
+    scene, _ = scene_cache("hf224", sah=True)
+    w, h = 640, 360
+    kw = dict(mode=1, depth=3, spp=2, seed=2, flags=clpt.FLAG_JITTER)
+    renderer.set_meshes(scene)
+    renderer.set_params(**kw)
+    renderer.create_image(w, h)
+    tilts = [-0.9, -0.9, -0.45, -0.45, -0.1, -0.1, 0.05, -0.6, -0.6]
+    for i, ty in enumerate(tilts):
+        fwd = np.array([0.0, ty, 0.9075])
+        cam = clpt.cam_matrix(clpt.make_camera(near=0.1, far=1.0, fov=np.pi / 3, position=(0.0, 0.9, -1.7),
+                                               forward=tuple(fwd / np.linalg.norm(fwd))), h)
+        renderer.set_camera_matrix(cam)
+        renderer.execute()
+        ref = oracle.render(scene, cam, w, h, aov=False, **kw)["rgba"]
+        _assert_bit_equal(renderer.read_image(), ref, f"frame {i} (tilt {ty})")
+
+
 def _unorm8(frame):
     """What write_imagef stores into a CL_UNORM_INT8 image: clamp, x255 in fp32, round to nearest even."""
     return np.rint(np.clip(frame, 0.0, 1.0).astype(np.float32) * np.float32(255.0)).astype(np.uint8)
