@@ -210,15 +210,22 @@ __device__ __forceinline__ float sah_cost(const float *ext, int ax, float left_e
     return cost;
 }
 
+// W lanes per node.  W = 8 serves the nodes of at most SMALL_MAX references (four nodes per warp:
+// near the leaves almost every node is that small, and a whole warp per node left most lanes
+// idle -- the kernel was half of the build); W = 32 serves the rest, two references per lane above 32.
+constexpr int SMALL_MAX = 8;
+
+template <int W>
 __global__ void __launch_bounds__(256)
 choose_kernel(const ANode *__restrict__ nodes, int n_nodes, const unsigned *__restrict__ hist,
               const int *__restrict__ ref_tri, const float *__restrict__ lo, const float *__restrict__ hi, int n_tris,
               int min_split, float ct, float ci, float empty_bonus, Decision *__restrict__ decisions) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (a >= n_nodes) return;
+    const int lane = threadIdx.x & 31, sub = lane & (W - 1);
+    const unsigned mask = W == 32 ? 0xffffffffu : (((1u << W) - 1u) << (lane & ~(W - 1)));
+    const int a = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) / W);
+    if (a >= n_nodes) return; // (whole groups leave together: `a` is uniform in a group)
     const ANode nd = nodes[a];
+    if ((W == 8) != (nd.count <= SMALL_MAX)) return; // the other launch's node
     Decision d;
     d.axis = -1;
     d.plane = 0.0f;
@@ -230,25 +237,51 @@ choose_kernel(const ANode *__restrict__ nodes, int n_nodes, const unsigned *__re
         float best = ci * (float)nd.count; // the cost of leaving the node a leaf
         int best_ax = -1;
         float best_plane = 0.0f;
-        const int t0 = lane < nd.count && nd.hist_slot < 0 ? ref_tri[nd.begin + lane] : -1;
-        const int t1 = lane + 32 < nd.count && nd.hist_slot < 0 ? ref_tri[nd.begin + lane + 32] : -1;
+        const bool exact = nd.hist_slot < 0;
+        const bool two = W == 32 && nd.count > 32; // a second reference per lane
+        const int t0 = exact && sub < nd.count ? ref_tri[nd.begin + sub] : -1;
+        const int t1 = exact && two && sub + 32 < nd.count ? ref_tri[nd.begin + sub + 32] : -1;
         for (int ax = 0; ax < 3; ax++) {
             if (!(ext[ax] > 0.0f) || !(inv_area > 0.0f)) continue;
             float c = 3.0e38f, p = 0.0f; // this lane's best candidate on this axis
-            if (nd.hist_slot < 0) {
-                // exact: every bound of every reference is a candidate
+            if (exact) {
+                // every bound of every reference is a candidate; a lane evaluates its own references' bounds
                 const float l0 = t0 >= 0 ? lo[(size_t)ax * n_tris + t0] : 0.0f, h0 = t0 >= 0 ? hi[(size_t)ax * n_tris + t0] : 0.0f;
-                const float l1 = t1 >= 0 ? lo[(size_t)ax * n_tris + t1] : 0.0f, h1 = t1 >= 0 ? hi[(size_t)ax * n_tris + t1] : 0.0f;
-                const float cand[4] = { l0, h0, l1, h1 };
-                int nl[4] = { 0, 0, 0, 0 }, nr[4] = { 0, 0, 0, 0 };
-                for (int j = 0; j < nd.count; j++) {
-                    const float lj = __shfl_sync(FULL, j < 32 ? l0 : l1, j & 31), hj = __shfl_sync(FULL, j < 32 ? h0 : h1, j & 31);
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        nr[k] += hj > cand[k] ? 1 : 0;
-                        nl[k] += (lj < cand[k] || !(hj > cand[k])) ? 1 : 0;
+                float l1 = 0.0f, h1 = 0.0f;
+                if (two && t1 >= 0) {
+                    l1 = lo[(size_t)ax * n_tris + t1];
+                    h1 = hi[(size_t)ax * n_tris + t1];
+                }
+                int nl0 = 0, nr0 = 0, nl1 = 0, nr1 = 0, nl2 = 0, nr2 = 0, nl3 = 0, nr3 = 0;
+                const int first_n = nd.count < W ? nd.count : W;
+                for (int j = 0; j < first_n; j++) {
+                    const float lj = __shfl_sync(mask, l0, j, W), hj = __shfl_sync(mask, h0, j, W);
+                    nr0 += hj > l0 ? 1 : 0;
+                    nl0 += (lj < l0 || !(hj > l0)) ? 1 : 0;
+                    nr1 += hj > h0 ? 1 : 0;
+                    nl1 += (lj < h0 || !(hj > h0)) ? 1 : 0;
+                    if (two) {
+                        nr2 += hj > l1 ? 1 : 0;
+                        nl2 += (lj < l1 || !(hj > l1)) ? 1 : 0;
+                        nr3 += hj > h1 ? 1 : 0;
+                        nl3 += (lj < h1 || !(hj > h1)) ? 1 : 0;
                     }
                 }
+                if (two) {
+                    for (int j = 32; j < nd.count; j++) {
+                        const float lj = __shfl_sync(mask, l1, j - 32, W), hj = __shfl_sync(mask, h1, j - 32, W);
+                        nr0 += hj > l0 ? 1 : 0;
+                        nl0 += (lj < l0 || !(hj > l0)) ? 1 : 0;
+                        nr1 += hj > h0 ? 1 : 0;
+                        nl1 += (lj < h0 || !(hj > h0)) ? 1 : 0;
+                        nr2 += hj > l1 ? 1 : 0;
+                        nl2 += (lj < l1 || !(hj > l1)) ? 1 : 0;
+                        nr3 += hj > h1 ? 1 : 0;
+                        nl3 += (lj < h1 || !(hj > h1)) ? 1 : 0;
+                    }
+                }
+                const float cand[4] = { l0, h0, l1, h1 };
+                const int nl[4] = { nl0, nl1, nl2, nl3 }, nr[4] = { nr0, nr1, nr2, nr3 };
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const bool present = k < 2 ? t0 >= 0 : t1 >= 0;
@@ -259,13 +292,13 @@ choose_kernel(const ANode *__restrict__ nodes, int n_nodes, const unsigned *__re
                         p = cand[k];
                     }
                 }
-            } else {
+            } else if (W == 32) {
                 const unsigned *h = hist + (size_t)nd.hist_slot * (3 * 2 * NBINS);
                 const unsigned s = h[(ax * 2 + 0) * NBINS + lane], e = h[(ax * 2 + 1) * NBINS + lane];
                 // exclusive prefix sums: plane k (k = lane, 1..31) sits at the low edge of bin k
                 unsigned ps = s, pe = e;
                 for (int off = 1; off < 32; off <<= 1) {
-                    const unsigned us = __shfl_up_sync(FULL, ps, off), ue = __shfl_up_sync(FULL, pe, off);
+                    const unsigned us = __shfl_up_sync(mask, ps, off), ue = __shfl_up_sync(mask, pe, off);
                     if (lane >= off) {
                         ps += us;
                         pe += ue;
@@ -282,9 +315,9 @@ choose_kernel(const ANode *__restrict__ nodes, int n_nodes, const unsigned *__re
                     }
                 }
             }
-            // warp argmin under the total order
-            for (int off = 16; off > 0; off >>= 1) {
-                const float oc = __shfl_xor_sync(FULL, c, off), op = __shfl_xor_sync(FULL, p, off);
+            // argmin over the node's lanes under the total order
+            for (int off = W / 2; off > 0; off >>= 1) {
+                const float oc = __shfl_xor_sync(mask, c, off, W), op = __shfl_xor_sync(mask, p, off, W);
                 if (better(oc, ax, op, c, ax, p)) {
                     c = oc;
                     p = op;
@@ -301,7 +334,7 @@ choose_kernel(const ANode *__restrict__ nodes, int n_nodes, const unsigned *__re
             d.plane = best_plane;
         }
     }
-    if (lane == 0) decisions[a] = d;
+    if (sub == 0) decisions[a] = d;
 }
 
 // ---- scans -----------------------------------------------------------------------------
@@ -645,7 +678,9 @@ bool clpt_gpu_build(const float4 *verts, int n_verts, const int4 *corners, int n
             bin_kernel<<<(n_refs + 255) / 256, 256, 0, s>>>(W.nodes[cur], W.ref_tri[cur], W.ref_node[cur], n_refs, W.lo,
                                                             W.hi, n_tris, min_split, W.hist);
         }
-        choose_kernel<<<(unsigned)(((size_t)n_nodes * 32 + 255) / 256), 256, 0, s>>>(
+        choose_kernel<32><<<(unsigned)(((size_t)n_nodes * 32 + 255) / 256), 256, 0, s>>>(
+            W.nodes[cur], n_nodes, W.hist, W.ref_tri[cur], W.lo, W.hi, n_tris, min_split, P.ct, P.ci, P.empty_bonus, W.dec);
+        choose_kernel<8><<<(unsigned)(((size_t)n_nodes * 8 + 255) / 256), 256, 0, s>>>(
             W.nodes[cur], n_nodes, W.hist, W.ref_tri[cur], W.lo, W.hi, n_tris, min_split, P.ct, P.ci, P.empty_bonus, W.dec);
         RefFlagFn rf{ W.nodes[cur], W.dec, W.ref_tri[cur], W.ref_node[cur], W.lo, W.hi, n_tris };
         scan(n_refs, rf, W.ref_scan, W.totals, s);

@@ -148,13 +148,16 @@ def test_fat_leaf_engine_bit_exact(clpt, oracle, renderer, scene_cache, name, tr
 
 
 def test_engine_is_chosen_per_tree(clpt, renderer, scene_cache):
-    """Automatic engine: the fat-leaf variant for trees whose triangles sit in fat leaves (the
-    reference builder at 100k triangles), the full-occupancy kernel for SAH trees."""
+    """Automatic engine: the fat-leaf variant for big trees whose triangles sit in fat leaves (the
+    reference builder from a few hundred thousand triangles up), the full-occupancy kernel for
+    small ones and for SAH trees."""
     L = clpt.lib()
     L.CLSetEngine(0)
     cam = _cam(clpt, "canonical", 48)
-    for sah, want in ((False, 2), (True, 1)):
-        scene, _ = scene_cache("hf224", sah=sah)
+    from clpathtracer_b200 import scenes
+
+    big = clpt.build_kd(*scenes.heightfield(520, False))  # 540,800 triangles, DEPTH 15: ~40 per leaf
+    for scene, want in ((big, 2), (scene_cache("hf224", sah=False)[0], 1), (scene_cache("hf224", sah=True)[0], 1)):
         _render_gpu(renderer, scene, cam, 64, 48, aov=False, mode=0, depth=2)
         assert L.CLLastEngine() == want
 
