@@ -81,9 +81,7 @@ def parse_args():
         "c2": dict(width=1920, height=1080, spp=16, depth=5, grid=224),
         "c3": dict(width=1920, height=1080, spp=64, depth=5, grid=707, tile_rows=8),
         # 4K progressive accumulation (1 spp per frame) of a 10M-triangle scene
-        # (row tiles of 32 rows: on the 1.5 GB scene a rank's share of the frame is then a set of
-        #  compacter terrain strips; measured -15% per-rank kernel time against 8-row tiles)
-        "c4": dict(width=3840, height=2160, spp=1, depth=5, grid=2236, progressive=True, tile_rows=32),
+        "c4": dict(width=3840, height=2160, spp=1, depth=5, grid=2236, progressive=True),
         # animated: per-frame object transform + kd rebuild + re-upload, 1080p at 4 spp (run_animated)
         "c5": dict(width=1920, height=1080, spp=4, depth=2, grid=158),
     }
@@ -102,9 +100,13 @@ def workload_config(a):
         "render_mode": a.mode, "kd_builder": ("reference heuristic (src/kd_tree.c:95-200) at depth %d, 25 bins" % a.tree_depth) if a.builder == "ref"
                       else "build_kd_sah ci=%g bonus=%g bins=%d" % (a.sah_ci, a.sah_bonus, a.sah_bins),
         "mode": "mirror (src/kernel.cl:399-417 enabled)",
-        "sharding": f"row tiles of {a.tile_rows} rows, round-robin over ranks, scene replicated; frame assembled by "
-                    + ("the render kernel storing into peer-mapped frames (NVLink), two one-word barriers per frame"
-                       if getattr(a, "direct_placement", 1) else "NCCL all-gather + de-interleave"),
+        "sharding": ("progressive frames are spread over ranks by SAMPLE: every rank renders the whole frame with its "
+                     "own sample indices into its own fixed-point sums (a step = ranks x spp samples per pixel); nothing "
+                     "crosses GPUs per frame, the read-back adds the ranks' sums (ncclAllReduce, 64-bit integers)")
+                    if a.progressive else
+                    (f"row tiles of {a.tile_rows} rows, round-robin over ranks, scene replicated; frame assembled by "
+                     + ("the render kernel storing into peer-mapped frames (NVLink), two flag-word barriers per frame"
+                        if getattr(a, "direct_placement", 1) else "NCCL all-gather + de-interleave")),
         "l2": "flushed between timed frames (CLFlushL2, 256 MiB overwrite, outside the timed events)",
     }
 
@@ -197,7 +199,7 @@ def oracle_flags(a):
     return 0 if a.no_jitter else op.FLAG_JITTER
 
 
-def oracle_check_and_baseline(a, scene, cam, gpu_frame, target_seconds, want_baseline):
+def oracle_check_and_baseline(a, scene, cam, gpu_frame, target_seconds, want_baseline, world=1):
     """One run of the oracle port (all host cores) serves two purposes: it is the
     `cpu_baseline` sample, and its frame is compared WORD FOR WORD with the frame the
     GPU path just rendered with the timed parameters (`parity`).  The whole frame at
@@ -209,36 +211,40 @@ def oracle_check_and_baseline(a, scene, cam, gpu_frame, target_seconds, want_bas
     from oracle import oracle_py as op
 
     cores = host_cores()
-    kw = dict(mode=oracle_mode(a), depth=a.depth, seed=a.seed, flags=oracle_flags(a), aov=False, threads=cores)
+    # a progressive frame on `world` ranks is world x spp samples per pixel (spread by sample), added to
+    # fixed-point sums; the check frame is the first frame after a reset, i.e. the mean of those samples
+    flags = oracle_flags(a) | (op.FLAG_ACCUMULATE if a.progressive else 0)
+    kw = dict(mode=oracle_mode(a), depth=a.depth, seed=a.seed, flags=flags, aov=False, threads=cores)
+    spp_frame = a.spp * (world if a.progressive else 1)
     t0 = time.time()
     r1 = op.render(scene, cam, a.width, a.height, spp=1, **kw)
     t1 = time.time() - t0
-    full = a.spp == 1 or t1 * a.spp <= 2.0 * target_seconds
+    full = spp_frame == 1 or t1 * spp_frame <= 2.0 * target_seconds
     baseline, parity = None, {"checked": False}
     if full:
-        if a.spp == 1:
+        if spp_frame == 1:
             ref, secs = r1, t1
         else:
             t0 = time.time()
-            ref = op.render(scene, cam, a.width, a.height, spp=a.spp, **kw)
+            ref = op.render(scene, cam, a.width, a.height, spp=spp_frame, **kw)
             secs = time.time() - t0
-        rays, spp, rows = ref["counters"]["rays"], a.spp, (0, a.height)
+        rays, spp, rows = ref["counters"]["rays"], spp_frame, (0, a.height)
     else:
-        spp = max(1, int(min(a.spp, target_seconds / max(t1, 1e-3))))
+        spp = max(1, int(min(spp_frame, target_seconds / max(t1, 1e-3))))
         if want_baseline and spp > 1:
             t0 = time.time()
             rb = op.render(scene, cam, a.width, a.height, spp=spp, **kw)
             secs, rays = time.time() - t0, rb["counters"]["rays"]
         else:
             secs, rays, spp = t1, r1["counters"]["rays"], 1
-        band = max(8, int(a.height * target_seconds / max(t1 * a.spp, 1e-3)) // 8 * 8)
+        band = max(8, int(a.height * target_seconds / max(t1 * spp_frame, 1e-3)) // 8 * 8)
         rows = (max(0, a.height // 2 - band // 2), min(a.height, a.height // 2 - band // 2 + band))
-        ref = op.render(scene, cam, a.width, a.height, spp=a.spp, rows=rows, **kw)
+        ref = op.render(scene, cam, a.width, a.height, spp=spp_frame, rows=rows, **kw)
     if want_baseline:
         baseline = {"value": round(rays / secs / 1e6, 4), "unit": UNIT, "cores": cores, "kind": "port",
-                    "sample": f"same scene/camera/depth, full {a.width}x{a.height} frame at {spp} of {a.spp} spp "
+                    "sample": f"same scene/camera/depth, full {a.width}x{a.height} frame at {spp} of {spp_frame} spp "
                               f"({rays} rays in {secs:.1f} s)",
-                    "ms_per_frame_at_full_spp": round(secs / spp * a.spp * 1e3, 1)}
+                    "ms_per_frame_at_full_spp": round(secs / spp * spp_frame * 1e3, 1)}
     if gpu_frame is not None:
         want = ref["rgba"][rows[0]:rows[1]]
         got = gpu_frame[rows[0]:rows[1]]
@@ -636,7 +642,8 @@ def main():
         e2e_value = rays_per_frame / (e2e_ms / a.steps * 1e-3) / 1e6
         peak, peak_src = hbm_peak()
         # roofline of the render kernel: algorithmic bytes of ONE launch on this rank / its duration
-        my_bytes = algorithmic_bytes(counters, len(cl_rows(a, rank, world)) * a.width)
+        my_rows = a.height if a.progressive else len(cl_rows(a, rank, world))
+        my_bytes = algorithmic_bytes(counters, my_rows * a.width)
         kernel_ms = float(np.mean(kern_ms))
         achieved = my_bytes / (kernel_ms * 1e-3) / 1e9
         # What binds: one ncu --set full capture per workload (profiles/binding.json, made by
@@ -695,7 +702,7 @@ def main():
         want_baseline = world == 1 and not a.no_cpu_baseline
         if want_baseline or not a.no_parity_check:
             baseline, parity = oracle_check_and_baseline(a, scene, cam, None if a.no_parity_check else check_frame,
-                                                         a.cpu_seconds, want_baseline)
+                                                         a.cpu_seconds, want_baseline, world)
         else:
             baseline, parity = None, {"checked": False}
         # every rank holds the whole frame: one sha per rank, to be compared with each other and,

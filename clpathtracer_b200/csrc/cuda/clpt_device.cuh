@@ -73,6 +73,13 @@ struct ClptFrame {
     int rank, nranks, tile_rows; // row-tile sharding; nranks == 1 -> whole image
     int local_rows;              // rows this rank renders (slab height)
     float4 *target;              // slab (nranks > 1) or the image itself
+    // Progressive frames (CLPT_F_ACCUMULATE): four 64-bit words per pixel of the WHOLE image -- the
+    // sums of the samples' r, g, b in 2^-32 fixed point and the sample count.  Integer sums do not
+    // depend on the order of the additions, so the accumulated frame is the same bits whether one
+    // GPU adds the samples one after the other or N GPUs each add every N-th sample and the
+    // read-back adds the N buffers (which is how progressive frames are spread over GPUs: by
+    // sample, every rank renders the whole frame).
+    unsigned long long *accum;
     // Direct placement across GPUs: when n_peer_images > 0, every finished pixel is also
     // stored at its image position in each of these full-size frames -- this rank's own
     // and, through peer mappings over NVLink, every other rank's -- so the frame is
@@ -93,6 +100,13 @@ struct ClptFrame {
 };
 
 #ifdef __CUDACC__
+// Sample colour -> 2^-32 fixed point, round to nearest even; negative and NaN -> 0, saturates at
+// 2^20 (oracle_kernel.c: fix32).  The product with 2^32 is exact.
+__device__ __forceinline__ unsigned long long clpt_fix32(float x) {
+    if (!(x > 0.0f)) return 0ull;
+    if (x >= 1048576.0f) return 1ull << 52;
+    return __float2ull_rn(x * 4294967296.0f);
+}
 // float in [0,1] -> UNORM8, round to nearest even, NaN -> 0: a UNORM8 image write.
 __device__ __forceinline__ unsigned clpt_to_unorm8(float v) {
     return (unsigned)__float2int_rn(__saturatef(v) * 255.0f);
@@ -108,7 +122,8 @@ int clpt_render_block_rows(const ClptFrame &frame); // rows of blocks the launch
 void clpt_launch_deinterleave(const float4 *gathered, float4 *image, int width, int height,
                               int nranks, int tile_rows, int slab_rows, cudaStream_t stream);
 void clpt_launch_fill(float4 *dst, size_t n, float value, cudaStream_t stream);
-void clpt_launch_normalise(const float4 *src, float4 *dst, size_t n, cudaStream_t stream);
+void clpt_launch_fill_u64(unsigned long long *dst, size_t n, cudaStream_t stream);
+void clpt_launch_normalise(const unsigned long long *accum, float4 *dst, size_t n, cudaStream_t stream);
 struct ClptFlagPeers {
     unsigned int *flags[CLPT_MAX_PEERS]; // rank r's barrier words (peer mappings; this rank's own at [rank])
 };
@@ -116,7 +131,5 @@ struct ClptFlagPeers {
 // array is written by src only.  Epochs only grow.
 void clpt_launch_flag_barrier(const ClptFlagPeers &peers, int rank, int nranks, unsigned int epoch,
                               cudaStream_t stream);
-void clpt_launch_pack_rgba8(const float4 *src, uchar4 *dst, size_t n, bool normalise, cudaStream_t stream);
-void clpt_launch_deinterleave_rgba8(const uchar4 *gathered, uchar4 *image, int width, int height, int nranks,
-                                    int tile_rows, int slab_rows, cudaStream_t stream);
+void clpt_launch_pack_rgba8(const float4 *src, uchar4 *dst, size_t n, cudaStream_t stream);
 const void *clpt_render_kernel_symbol(void);

@@ -404,14 +404,11 @@ __device__ __forceinline__ int slab_row_to_image_row(const ClptFrame &F, int ly)
     return (lt * F.nranks + F.rank) * F.tile_rows + (ly - lt * F.tile_rows);
 }
 
-// Final store of a pixel's ordered sample sum (shared by both engines).
+// Final store of a pixel's ordered sample sum.
 __device__ __forceinline__ void store_pixel(const ClptFrame &F, int x, int ly, V3 acc, int spp) {
     float4 *dst = F.target + (size_t)ly * F.width + x;
     float4 out;
-    if (F.flags & CLPT_F_ACCUMULATE) {
-        const float4 prev = *dst;
-        out = make_float4(fadd(prev.x, acc.x), fadd(prev.y, acc.y), fadd(prev.z, acc.z), fadd(prev.w, (float)spp));
-    } else if (spp == 1) {
+    if (spp == 1) {
         out = make_float4(acc.x, acc.y, acc.z, 1.0f);
     } else {
         const float k = fdiv(1.0f, (float)spp);
@@ -422,6 +419,19 @@ __device__ __forceinline__ void store_pixel(const ClptFrame &F, int x, int ly, V
         const size_t at = (size_t)slab_row_to_image_row(F, ly) * F.width + x;
         for (int r = 0; r < F.n_peer_images; r++) F.peer_image[r][at] = out;
     }
+}
+
+// Progressive frames: add this frame's samples of a pixel to the fixed-point sums.
+__device__ __forceinline__ void accumulate_pixel(const ClptFrame &F, int x, int y, unsigned long long r,
+                                                 unsigned long long g, unsigned long long b, int spp) {
+    ulonglong2 *p = reinterpret_cast<ulonglong2 *>(F.accum + 4 * ((size_t)y * F.width + x));
+    ulonglong2 rg = p[0], bn = p[1];
+    rg.x += r;
+    rg.y += g;
+    bn.x += b;
+    bn.y += (unsigned long long)spp;
+    p[0] = rg;
+    p[1] = bn;
 }
 
 } // namespace

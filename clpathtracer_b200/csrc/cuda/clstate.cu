@@ -160,7 +160,9 @@ struct {
     int width = 0, height = 0;
     bool headless = false, have_image = false;
     DevBuf<float4> image, slab, gathered, scratch;
-    DevBuf<uchar4> slab8, gathered8; // texel twins of slab / gathered (progressive read-back across GPUs)
+    // progressive frames: 2^-32 fixed-point sums + sample count, four words per pixel of the whole
+    // image (ClptFrame::accum); accum_sum = the ranks' buffers added up for a read-back
+    DevBuf<unsigned long long> accum, accum_sum;
     bool aov = false;
     DevBuf<int> aov_prim;
     DevBuf<float> aov_t;
@@ -500,41 +502,43 @@ void alloc_targets() {
         CU(cudaMemsetAsync(St.aov_uv.ptr, 0, px * sizeof(float2), St.stream));
     }
     St.scratch.release();
+    St.accum.release();
+    St.accum_sum.release();
     St.sample_base = 0;
     CU(cudaStreamSynchronize(St.stream));
     p2p_setup();
 }
 
-// True when the ranks accumulate in their own slabs and nothing crosses GPUs per frame
-// ("Progressive accumulation: accumulate locally per rank; gather only
-// on display/readback").
-bool accumulates_locally() { return (St.flags & CLPT_FLAG_ACCUMULATE) && St.nranks > 1; }
+// Progressive frames are spread over GPUs by SAMPLE: every rank renders the whole frame with its own
+// sample indices into its own fixed-point buffer, nothing crosses GPUs per frame, and a read-back
+// adds the buffers up ("accumulate locally per rank; gather only on
+// display/readback").  Integer sums are order-free, so the result is the single-GPU frame bit for bit.
+bool sample_parallel() { return (St.flags & CLPT_FLAG_ACCUMULATE) && St.nranks > 1; }
+
+void ensure_accum() {
+    const size_t words = (size_t)St.width * St.height * 4;
+    if (St.accum.count != words) {
+        St.accum.resize(words);
+        clpt_launch_fill_u64(St.accum.ptr, words, St.stream);
+        St.sample_base = 0;
+    }
+}
 
 // The current frame as displayable float4 (rgb, 1) on the library's stream.  Replace mode: the
-// frame itself.  Progressive mode: sum / count into `scratch`; across GPUs the ranks' slabs are
-// gathered first (ncclAllGather + de-interleave), which makes the call COLLECTIVE in that case.
+// frame itself.  Progressive mode: sums / count into `scratch`; across GPUs the ranks' buffers are
+// added first (ncclAllReduce, 64-bit integer sum), which makes the call COLLECTIVE in that case.
 const float4 *displayable_frame() {
     const size_t px = (size_t)St.width * St.height;
     if (!(St.flags & CLPT_FLAG_ACCUMULATE)) return St.image.ptr;
+    ensure_accum();
     if (St.scratch.count != px) St.scratch.resize(px);
-    if (St.nranks > 1) {
-        const size_t slab_px = (size_t)slab_rows_for(St.height) * St.width;
-        if (St.gathered.count != slab_px * St.nranks) {
-            St.gathered.resize(slab_px * St.nranks);
-            CU(cudaMemsetAsync(St.gathered.ptr, 0, slab_px * St.nranks * sizeof(float4), St.stream));
-        }
-        if (St.comm) {
-            NC(g_nccl.AllGather(St.slab.ptr, St.gathered.ptr, slab_px * 4, ncclFloat, St.comm, St.stream));
-        } else { // sharded without a communicator: this rank's rows only
-            CU(cudaMemcpyAsync(St.gathered.ptr + slab_px * St.rank, St.slab.ptr, slab_px * sizeof(float4),
-                               cudaMemcpyDeviceToDevice, St.stream));
-        }
-        clpt_launch_deinterleave(St.gathered.ptr, St.scratch.ptr, St.width, St.height, St.nranks, St.tile_rows,
-                                 slab_rows_for(St.height), St.stream);
-        clpt_launch_normalise(St.scratch.ptr, St.scratch.ptr, px, St.stream);
-    } else {
-        clpt_launch_normalise(St.image.ptr, St.scratch.ptr, px, St.stream);
-    }
+    const unsigned long long *sums = St.accum.ptr;
+    if (St.nranks > 1 && St.comm) {
+        if (St.accum_sum.count != px * 4) St.accum_sum.resize(px * 4);
+        NC(g_nccl.AllReduce(St.accum.ptr, St.accum_sum.ptr, px * 4, ncclUint64, ncclSum, St.comm, St.stream));
+        sums = St.accum_sum.ptr;
+    } // (sharded without a communicator: this rank's samples only)
+    clpt_launch_normalise(sums, St.scratch.ptr, px, St.stream);
     CU(cudaGetLastError());
     return St.scratch.ptr;
 }
@@ -571,20 +575,9 @@ void enqueue_read(void *dst, size_t bytes, int format) {
     // the copy that last used this staging buffer must have drained before it is rewritten
     if (slot.in_flight) CU(cudaStreamWaitEvent(St.stream, slot.done, 0));
     if (slot.staging.count < bytes) slot.staging.resize(bytes);
-    if (format == CLPT_READ_RGBA8 && accumulates_locally() && St.comm) {
-        // progressive frame across GPUs, texel read-back: every rank normalises and packs its OWN
-        // slab first, so 4 bytes per pixel cross NVLink instead of 16 (collective)
-        const size_t slab_px = (size_t)slab_rows_for(St.height) * St.width;
-        if (St.slab8.count != slab_px) St.slab8.resize(slab_px);
-        if (St.gathered8.count != slab_px * St.nranks) St.gathered8.resize(slab_px * St.nranks);
-        clpt_launch_pack_rgba8(St.slab.ptr, St.slab8.ptr, slab_px, true, St.stream);
-        NC(g_nccl.AllGather(St.slab8.ptr, St.gathered8.ptr, slab_px * 4, ncclChar, St.comm, St.stream));
-        clpt_launch_deinterleave_rgba8(St.gathered8.ptr, reinterpret_cast<uchar4 *>(slot.staging.ptr), St.width,
-                                       St.height, St.nranks, St.tile_rows, slab_rows_for(St.height), St.stream);
-        CU(cudaGetLastError());
-    } else if (format == CLPT_READ_RGBA8) {
+    if (format == CLPT_READ_RGBA8) {
         const float4 *src = displayable_frame();
-        clpt_launch_pack_rgba8(src, reinterpret_cast<uchar4 *>(slot.staging.ptr), (size_t)St.width * St.height, false,
+        clpt_launch_pack_rgba8(src, reinterpret_cast<uchar4 *>(slot.staging.ptr), (size_t)St.width * St.height,
                                St.stream);
         CU(cudaGetLastError());
     } else {
@@ -651,7 +644,7 @@ void clpt_state_launch_frame(int width, int height) {
     // (measured: +3..4% on an eighth of the bench frame, -1% on the whole of it).
     F.log2_warps_per_pixel = 0;
     {
-        const int rows = St.nranks > 1 ? local_rows_for(height) : height;
+        const int rows = F.local_rows;
         const double claims_per_warp = (double)rows * width / ((double)St.prop.multiProcessorCount * 64.0);
         if (claims_per_warp < 150.0) {
             while (F.log2_warps_per_pixel < 3 && (64 << F.log2_warps_per_pixel) <= St.spp) F.log2_warps_per_pixel++;
@@ -664,12 +657,24 @@ void clpt_state_launch_frame(int width, int height) {
     }
     F.seed = St.seed;
     F.sample_base = St.sample_base;
+    F.accum = nullptr;
     F.max_leaf_visits = St.max_leaf_visits;
     F.rank = St.rank;
     F.nranks = St.nranks;
     F.tile_rows = St.tile_rows;
     F.local_rows = St.nranks > 1 ? local_rows_for(height) : height;
     F.target = St.nranks > 1 ? St.slab.ptr : St.image.ptr;
+    const int spp_frame = St.spp < 1 ? 1 : St.spp;
+    if (St.flags & CLPT_FLAG_ACCUMULATE) {
+        // progressive: the whole frame on every rank, rank r takes samples base + r*spp .. + spp - 1
+        ensure_accum();
+        F.accum = St.accum.ptr;
+        F.rank = 0;
+        F.nranks = 1;
+        F.local_rows = height;
+        F.target = St.image.ptr; // (not written)
+        F.sample_base = St.sample_base + (unsigned)(St.rank * spp_frame);
+    }
     F.aov_prim = St.aov ? St.aov_prim.ptr : nullptr;
     F.aov_t = St.aov ? St.aov_t.ptr : nullptr;
     F.aov_uv = St.aov ? St.aov_uv.ptr : nullptr;
@@ -678,7 +683,7 @@ void clpt_state_launch_frame(int width, int height) {
     F.work_counter = St.work_counter.ptr;
     F.blocks_x = F.n_warp_tiles = 0;
     F.row_cost = nullptr;
-    const bool local_only = accumulates_locally(); // progressive across GPUs: nothing crosses GPUs per frame
+    const bool local_only = sample_parallel(); // progressive across GPUs: nothing crosses GPUs per frame
     const bool p2p = St.p2p && St.comm && St.nranks > 1 && !local_only;
     F.n_peer_images = p2p ? St.nranks : 0;
     for (int r = 0; r < CLPT_MAX_PEERS; r++) F.peer_image[r] = p2p ? St.peer_image[r] : nullptr;
@@ -734,7 +739,7 @@ void clpt_state_launch_frame(int width, int height) {
     if (p2p) {
         flag_barrier(); // every rank's pixels have landed in this rank's frame
     } else if (local_only) {
-        // the slab holds this rank's running sums; CLReadImage* gathers (displayable_frame)
+        // this rank's samples went into its own sums; CLReadImage* adds the ranks' buffers (displayable_frame)
     } else if (St.nranks > 1 && St.comm) {
         const size_t slab_px = (size_t)slab_rows_for(height) * width;
         if (St.gathered.count != slab_px * St.nranks) St.gathered.resize(slab_px * St.nranks);
@@ -775,7 +780,7 @@ void clpt_state_launch_frame(int width, int height) {
     if (St.flags & CLPT_FLAG_COUNTERS) {
         CU(cudaMemcpy(St.host_counters, St.counters.ptr, sizeof(St.host_counters), cudaMemcpyDeviceToHost));
     }
-    if (St.flags & CLPT_FLAG_ACCUMULATE) St.sample_base += (unsigned)(St.spp < 1 ? 1 : St.spp);
+    if (St.flags & CLPT_FLAG_ACCUMULATE) St.sample_base += (unsigned)(spp_frame * St.nranks);
 }
 
 cudaStream_t clpt_state_stream() { return St.stream; }
@@ -851,8 +856,8 @@ void CLTerminate(void) {
     St.slab.release();
     St.gathered.release();
     St.scratch.release();
-    St.slab8.release();
-    St.gathered8.release();
+    St.accum.release();
+    St.accum_sum.release();
     St.aov_prim.release();
     St.aov_t.release();
     St.aov_uv.release();
@@ -1132,8 +1137,8 @@ void CLDeleteImage(void) {
     St.slab.release();
     St.gathered.release();
     St.scratch.release();
-    St.slab8.release();
-    St.gathered8.release();
+    St.accum.release();
+    St.accum_sum.release();
     St.aov_prim.release();
     St.aov_t.release();
     St.aov_uv.release();
@@ -1164,8 +1169,7 @@ void CLCreateImage(unsigned int texture) {
 void CLResetAccumulation(void) {
     require_init("CLResetAccumulation");
     if (!St.have_image) return;
-    clpt_launch_fill(St.image.ptr, St.image.count, 0.0f, St.stream);
-    if (St.slab.ptr) clpt_launch_fill(St.slab.ptr, St.slab.count, 0.0f, St.stream);
+    if (St.accum.ptr) clpt_launch_fill_u64(St.accum.ptr, St.accum.count, St.stream);
     CU(cudaStreamSynchronize(St.stream));
     St.sample_base = 0;
 }

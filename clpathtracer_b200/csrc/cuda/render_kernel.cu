@@ -154,6 +154,7 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
     float *const my_stage = stage + group * 3 * row_len; // this group's three channel rows
     const int my_col = member * 32 + lane;               // this lane's column in them
     const bool per_channel = s_lanes >= 4;
+    const bool accumulate = (F.flags & CLPT_F_ACCUMULATE) != 0;
     // Persistent warps: the grid only fills the machine; every warp (group) claims warp tiles
     // from a global counter until none are left.  Blocks cost anything from nothing
     // (sky) to hundreds of microseconds (grazing ground), and with one tile per warp
@@ -195,6 +196,8 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
         const bool valid = x < F.width && y < F.height && ly < F.local_rows;
         const unsigned pixel = (unsigned)(y * F.width + x);
         V3 acc = mk(0.0f, 0.0f, 0.0f); // per_channel: only .x is used, for channel `sslot`
+        // progressive frames sum the samples in 2^-32 fixed point (order-free, see ClptFrame::accum)
+        unsigned long long fx = 0ull, fy = 0ull, fz = 0ull; // per_channel: only fx is used
         const int round_samples = s_lanes << log2_g;
         for (int base = 0; base < spp; base += round_samples) {
             const int s = base + (member << log2_s) + sslot; // (member > 0 only when s_lanes == 32)
@@ -219,12 +222,23 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
                 if (per_channel) {
                     if (sslot < 3) {
                         const float *src = my_stage + sslot * row_len + group_base;
-                        for (int j = 0; j < in_round; j++) acc.x = fadd(acc.x, src[j]);
+                        if (accumulate) {
+                            for (int j = 0; j < in_round; j++) fx += clpt_fix32(src[j]);
+                        } else {
+                            for (int j = 0; j < in_round; j++) acc.x = fadd(acc.x, src[j]);
+                        }
                     }
                 } else if (sslot == 0) {
                     for (int j = 0; j < in_round; j++) {
-                        acc = vadd(acc, mk(my_stage[0 * row_len + group_base + j], my_stage[1 * row_len + group_base + j],
-                                           my_stage[2 * row_len + group_base + j]));
+                        const V3 c = mk(my_stage[0 * row_len + group_base + j], my_stage[1 * row_len + group_base + j],
+                                        my_stage[2 * row_len + group_base + j]);
+                        if (accumulate) {
+                            fx += clpt_fix32(c.x);
+                            fy += clpt_fix32(c.y);
+                            fz += clpt_fix32(c.z);
+                        } else {
+                            acc = vadd(acc, c);
+                        }
                     }
                 }
             }
@@ -232,12 +246,21 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
         }
         if (member == 0) {
             if (per_channel) { // bring the three channel sums to the group's first lane
-                const float r = __shfl_sync(0xffffffffu, acc.x, group_base);
-                const float g = __shfl_sync(0xffffffffu, acc.x, group_base + 1);
-                const float bl = __shfl_sync(0xffffffffu, acc.x, group_base + 2);
-                acc = mk(r, g, bl);
+                if (accumulate) {
+                    fy = __shfl_sync(0xffffffffu, fx, group_base + 1);
+                    fz = __shfl_sync(0xffffffffu, fx, group_base + 2);
+                    fx = __shfl_sync(0xffffffffu, fx, group_base);
+                } else {
+                    const float r = __shfl_sync(0xffffffffu, acc.x, group_base);
+                    const float g = __shfl_sync(0xffffffffu, acc.x, group_base + 1);
+                    const float bl = __shfl_sync(0xffffffffu, acc.x, group_base + 2);
+                    acc = mk(r, g, bl);
+                }
             }
-            if (valid && sslot == 0) store_pixel(F, x, ly, acc, spp);
+            if (valid && sslot == 0) {
+                if (accumulate) accumulate_pixel(F, x, y, fx, fy, fz, spp);
+                else store_pixel(F, x, ly, acc, spp);
+            }
             if (lane == 0 && F.row_cost) {
                 atomicAdd(F.row_cost + tile_row[warp], (unsigned long long)((unsigned)clock() - tile_t0[warp]));
             }
@@ -254,7 +277,7 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
     }
 }
 
-// Gathered slabs [rank][slab_rows][width] -> image rows (float4 pixels or RGBA8 texels).
+// Gathered slabs [rank][slab_rows][width] -> image rows.
 template <typename PX>
 __global__ void deinterleave_kernel(const PX *__restrict__ gathered, PX *__restrict__ image,
                                     int width, int height, int nranks, int tile_rows,
@@ -272,35 +295,31 @@ __global__ void fill_kernel(float4 *dst, size_t n, float value) {
     if (i < n) dst[i] = make_float4(value, value, value, value);
 }
 
-// Progressive target (sum, count in .w) -> displayable average.
-__global__ void normalise_kernel(const float4 *__restrict__ src, float4 *__restrict__ dst, size_t n) {
+// Progressive target (fixed-point sums + sample count) -> displayable average.
+__global__ void normalise_kernel(const unsigned long long *__restrict__ accum, float4 *__restrict__ dst, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float4 s = src[i];
-    if (s.w > 0.0f) {
-        const float k = __fdiv_rn(1.0f, s.w);
-        dst[i] = make_float4(__fmul_rn(s.x, k), __fmul_rn(s.y, k), __fmul_rn(s.z, k), 1.0f);
+    const ulonglong2 rg = reinterpret_cast<const ulonglong2 *>(accum)[2 * i], bn = reinterpret_cast<const ulonglong2 *>(accum)[2 * i + 1];
+    if (bn.y > 0ull) {
+        const double k = (double)bn.y * 4294967296.0; // (one IEEE division per channel, as the oracle's mean)
+        dst[i] = make_float4((float)((double)rg.x / k), (float)((double)rg.y / k), (float)((double)bn.x / k), 1.0f);
     } else {
         dst[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 }
 
+__global__ void fill_u64_kernel(unsigned long long *dst, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = 0ull;
+}
+
 // Displayable float4 frame -> RGBA8 UNORM texels, the format of the reference's render
 // target (src/GLHandler.c:177-185): what write_imagef does to a CL_UNORM_INT8 image,
 // clamp to [0,1], scale by 255, round to nearest even.
-// normalise != 0: src holds running sums with the sample count in .w (progressive frames).
-__global__ void pack_rgba8_kernel(const float4 *__restrict__ src, uchar4 *__restrict__ dst, size_t n, int normalise) {
+__global__ void pack_rgba8_kernel(const float4 *__restrict__ src, uchar4 *__restrict__ dst, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float4 c = src[i];
-    if (normalise) {
-        if (c.w > 0.0f) {
-            const float k = __fdiv_rn(1.0f, c.w);
-            c = make_float4(__fmul_rn(c.x, k), __fmul_rn(c.y, k), __fmul_rn(c.z, k), 1.0f);
-        } else {
-            c = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        }
-    }
+    const float4 c = src[i];
     dst[i] = make_uchar4((unsigned char)clpt_to_unorm8(c.x), (unsigned char)clpt_to_unorm8(c.y),
                          (unsigned char)clpt_to_unorm8(c.z), (unsigned char)clpt_to_unorm8(c.w));
 }
@@ -372,22 +391,19 @@ void clpt_launch_deinterleave(const float4 *gathered, float4 *image, int width, 
                                                                                  nranks, tile_rows, slab_rows);
 }
 
-void clpt_launch_deinterleave_rgba8(const uchar4 *gathered, uchar4 *image, int width, int height, int nranks,
-                                    int tile_rows, int slab_rows, cudaStream_t stream) {
-    const size_t n = (size_t)width * height;
-    if (n == 0) return;
-    deinterleave_kernel<uchar4><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(gathered, image, width, height,
-                                                                                 nranks, tile_rows, slab_rows);
-}
-
 void clpt_launch_fill(float4 *dst, size_t n, float value, cudaStream_t stream) {
     if (n == 0) return;
     fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dst, n, value);
 }
 
-void clpt_launch_normalise(const float4 *src, float4 *dst, size_t n, cudaStream_t stream) {
+void clpt_launch_normalise(const unsigned long long *accum, float4 *dst, size_t n, cudaStream_t stream) {
     if (n == 0) return;
-    normalise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, dst, n);
+    normalise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(accum, dst, n);
+}
+
+void clpt_launch_fill_u64(unsigned long long *dst, size_t n, cudaStream_t stream) {
+    if (n == 0) return;
+    fill_u64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dst, n);
 }
 
 void clpt_launch_flag_barrier(const ClptFlagPeers &peers, int rank, int nranks, unsigned int epoch,
@@ -395,9 +411,9 @@ void clpt_launch_flag_barrier(const ClptFlagPeers &peers, int rank, int nranks, 
     flag_barrier_kernel<<<1, 32, 0, stream>>>(peers, rank, nranks, epoch);
 }
 
-void clpt_launch_pack_rgba8(const float4 *src, uchar4 *dst, size_t n, bool normalise, cudaStream_t stream) {
+void clpt_launch_pack_rgba8(const float4 *src, uchar4 *dst, size_t n, cudaStream_t stream) {
     if (n == 0) return;
-    pack_rgba8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, dst, n, normalise ? 1 : 0);
+    pack_rgba8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, dst, n);
 }
 
 const void *clpt_render_kernel_symbol(void) {

@@ -91,7 +91,10 @@ enum {
 };
 enum {
     CLPT_FLAG_JITTER = 1,     /* sub-pixel jitter (implied by spp > 1 is NOT automatic: set it) */
-    CLPT_FLAG_ACCUMULATE = 2, /* progressive: add spp samples per frame into the target */
+    CLPT_FLAG_ACCUMULATE = 2, /* progressive: every frame adds its samples to per-pixel running sums
+                               * (2^-32 fixed point, so the sums do not depend on the order of the
+                               * additions); with N ranks a frame is N x spp samples per pixel --
+                               * rank r renders the WHOLE frame with samples base + r*spp .. */
     CLPT_FLAG_COUNTERS = 4    /* instrumented launch: fill the work counters */
 };
 
@@ -157,13 +160,15 @@ void CLSetMaxLeafVisits(int cap);          /* rope-hop cap per ray; default 4096
 void CLSetEngine(int engine);
 int CLLastEngine(void);                    /* engine the last CLExecute used: 1 or 2 */
 void CLCreateImageHeadless(int width, int height); /* float4 target, zeroed */
-void CLResetAccumulation(void);            /* zero the target and the sample counter */
+void CLResetAccumulation(void);            /* zero the running sums and the sample counter */
 /* Blocking device->host copy of the whole float4 frame (bytes must be
- * width*height*16).  With CLPT_FLAG_ACCUMULATE the running sum is normalised
- * by the sample count on the way out.  Across GPUs a progressive frame is
- * accumulated in each rank's own rows and gathered here (ncclAllGather), which
- * makes the CLReadImage* calls COLLECTIVE while CLPT_FLAG_ACCUMULATE is set and
- * a communicator is live; in every other case only the calling rank pays. */
+ * width*height*16).  With CLPT_FLAG_ACCUMULATE the running sums are divided by
+ * the sample count on the way out.  Across GPUs progressive frames are spread by
+ * sample, every rank keeps its own sums, and the read-back adds them
+ * (ncclAllReduce of 64-bit integers: the same bits as one GPU adding all the
+ * samples), which makes the CLReadImage* calls COLLECTIVE while
+ * CLPT_FLAG_ACCUMULATE is set and a communicator is live; in every other case
+ * only the calling rank pays. */
 void CLReadImage(float *dst_rgba, size_t bytes);
 /* The same frame as RGBA8 UNORM texels -- the format of the reference's render
  * target (src/GLHandler.c:177-185; what write_imagef stores: clamp, x255, round to

@@ -108,6 +108,8 @@ typedef struct oracle_params {
     float *normal;    /* 3 floats per pixel */
     float *path_edge; /* min over the hits of sample 0's path of min(u, v, |1-u-v|): how close the
                        * path came to a triangle edge (classifies tie-break mismatches); 2 = no hit */
+    uint64_t *accum;  /* ORACLE_ACCUMULATE: 4 words per pixel, the running sums of r, g, b in 2^-32
+                       * fixed point and the sample count; `rgba` then receives the mean so far */
     /* work counters, summed over all rays: rays, splits, leaves, tri tests,
      * vn-shaded hits, rays stopped by the cap */
     uint64_t counters[6];
@@ -295,6 +297,17 @@ void oracle_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]
     philox4x32_10(out, key[0], key[1]);
 }
 
+/* EXTENSION (progressive accumulation has no reference behaviour; this is the definition).
+ * A sample's colour enters the running sum as 2^-32 fixed point, rounded to nearest even;
+ * negative and NaN count as 0, values saturate at 2^20.  Integer sums do not depend on the order
+ * of the additions, so one device adding samples 0,1,2,... and N devices adding every N-th
+ * sample each produce the same bits. */
+static inline uint64_t fix32(float x) {
+    if (!(x > 0.0f)) return 0;
+    if (x >= 1048576.0f) return (uint64_t)1 << 52;
+    return (uint64_t)llrintf(x * 4294967296.0f);
+}
+
 static inline float u01(uint32_t x) { return (float)(x >> 8) * 0x1p-24f; } /* [0,1), exact */
 
 #define ORACLE_KEY1 0x636c7074u
@@ -396,6 +409,7 @@ static f3 shade_sample(const oracle_params *P, ray_t r, uint32_t pixel, uint32_t
 
 int oracle_render(oracle_params *P) {
     const int W = P->width, H = P->height;
+    if ((P->flags & ORACLE_ACCUMULATE) && (!P->accum || !P->rgba)) return 1;
     const float *M = P->cam;
     int spp = P->spp < 1 ? 1 : P->spp;
     int jitter = (P->flags & ORACLE_JITTER) != 0;
@@ -413,6 +427,7 @@ int oracle_render(oracle_params *P) {
                 /* kernel.cl:443-445: eye = column 2 of the inverse / w */
                 f3 origin = v3(M[2] / M[14], M[6] / M[14], M[10] / M[14]);
                 f3 acc = v3(0, 0, 0);
+                uint64_t fsum[3] = { 0, 0, 0 };
                 hit_t first;
                 float edge = 2.0f;
                 memset(&first, 0, sizeof(first));
@@ -433,12 +448,19 @@ int oracle_render(oracle_params *P) {
                     ray_t r = make_ray(origin, dir);
                     f3 c = shade_sample(P, r, pixel, sample, s == 0 ? &first : NULL, s == 0 ? &edge : NULL, cnt);
                     acc = add3(acc, c);
+                    fsum[0] += fix32(c.x);
+                    fsum[1] += fix32(c.y);
+                    fsum[2] += fix32(c.z);
                 }
                 size_t o = (size_t)y * (size_t)W + (size_t)x;
                 if (P->rgba) {
                     float *px = P->rgba + 4 * o;
                     if (P->flags & ORACLE_ACCUMULATE) {
-                        px[0] += acc.x; px[1] += acc.y; px[2] += acc.z; px[3] += (float)spp;
+                        uint64_t *a = P->accum + 4 * o;
+                        a[0] += fsum[0]; a[1] += fsum[1]; a[2] += fsum[2]; a[3] += (uint64_t)spp;
+                        const double k = (double)a[3] * 4294967296.0;
+                        px[0] = (float)((double)a[0] / k); px[1] = (float)((double)a[1] / k);
+                        px[2] = (float)((double)a[2] / k); px[3] = 1.0f;
                     } else if (spp == 1) {
                         px[0] = acc.x; px[1] = acc.y; px[2] = acc.z; px[3] = 1.0f;
                     } else {

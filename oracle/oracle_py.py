@@ -34,7 +34,7 @@ class OracleParams(C.Structure):
         ("materials", C.c_void_p), ("tri_material", C.c_void_p),
         ("n_materials", C.c_int32), ("reserved", C.c_int32),
         ("rgba", C.c_void_p), ("prim_id", C.c_void_p), ("t_hit", C.c_void_p),
-        ("uv", C.c_void_p), ("normal", C.c_void_p), ("path_edge", C.c_void_p),
+        ("uv", C.c_void_p), ("normal", C.c_void_p), ("path_edge", C.c_void_p), ("accum", C.c_void_p),
         ("counters", C.c_uint64 * 6),
     ]
 
@@ -94,6 +94,11 @@ def philox(ctr, key) -> np.ndarray:
     return out
 
 
+def new_accumulator(width: int, height: int) -> np.ndarray:
+    """Zeroed progressive state for render(..., flags=FLAG_ACCUMULATE, accumulate_into=...)."""
+    return np.zeros((height, width, 4), dtype=np.uint64)
+
+
 COUNTER_NAMES = ["rays", "splits", "leaves", "tris", "shade_vn", "capped"]
 
 
@@ -129,12 +134,17 @@ def render(scene, cam: np.ndarray, width: int, height: int, mode: int = 0, depth
             keep.append(tm)
             P.tri_material = tm.ctypes.data
     out = {}
-    if accumulate_into is not None:
-        rgba = accumulate_into
-    else:
-        rgba = np.zeros((height, width, 4), dtype=np.float32)
+    rgba = np.zeros((height, width, 4), dtype=np.float32)
     out["rgba"] = rgba
     P.rgba = rgba.ctypes.data
+    if flags & FLAG_ACCUMULATE:
+        # progressive: `accumulate_into` is the uint64[h, w, 4] running state (fixed-point sums of
+        # r, g, b and the sample count); out["rgba"] is the mean after this call, rows rendered only
+        if accumulate_into is None:
+            accumulate_into = new_accumulator(width, height)
+        assert accumulate_into.dtype == np.uint64 and accumulate_into.shape == (height, width, 4)
+        out["accum"] = accumulate_into
+        P.accum = accumulate_into.ctypes.data
     if aov:
         out["prim"] = np.full((height, width), -1, dtype=np.int32)
         out["t"] = np.zeros((height, width), dtype=np.float32)

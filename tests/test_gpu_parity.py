@@ -280,6 +280,9 @@ def test_path_mode_extension(clpt, oracle, renderer, scene_cache):
 
 
 def test_progressive_accumulation(clpt, oracle, renderer, scene_cache):
+    """Progressive frames add their samples to 2^-32 fixed-point sums (order-free integer
+    additions); the read-back is the mean.  Same bits as the oracle's, whatever the grouping of
+    the samples into frames."""
     scene, _ = scene_cache("hf22n")
     cam = _cam(clpt, "canonical", 120)
     flags = clpt.FLAG_JITTER | clpt.FLAG_ACCUMULATE
@@ -287,20 +290,22 @@ def test_progressive_accumulation(clpt, oracle, renderer, scene_cache):
     renderer.set_camera_matrix(cam)
     renderer.set_params(mode=1, depth=2, spp=2, seed=3, flags=flags)
     renderer.create_image(160, 120)
-    acc = np.zeros((120, 160, 4), dtype=np.float32)
+    acc = oracle.new_accumulator(160, 120)
     for frame in range(3):
         renderer.execute()
-        oracle.render(scene, cam, 160, 120, mode=1, depth=2, spp=2, seed=3, flags=flags, sample_base=2 * frame,
-                      accumulate_into=acc, aov=False)
-    img = renderer.read_image()
-    want = acc.copy()
-    want[..., :3] = acc[..., :3] * (np.float32(1.0) / acc[..., 3:4])
-    want[..., 3] = 1.0
-    _assert_bit_equal(img, want, "accumulated rgba")
+        want = oracle.render(scene, cam, 160, 120, mode=1, depth=2, spp=2, seed=3, flags=flags, sample_base=2 * frame,
+                             accumulate_into=acc, aov=False)["rgba"]
+    _assert_bit_equal(renderer.read_image(), want, "accumulated rgba")
+    # the same six samples in one oracle call, and as 3 + 3: the sums do not depend on the grouping
+    once = oracle.render(scene, cam, 160, 120, mode=1, depth=2, spp=6, seed=3, flags=flags, aov=False)
+    assert np.array_equal(once["accum"], acc)
+    _assert_bit_equal(once["rgba"], want, "grouping")
+    assert np.abs(want - oracle.render(scene, cam, 160, 120, mode=1, depth=2, spp=6, seed=3, flags=clpt.FLAG_JITTER,
+                                       aov=False)["rgba"]).max() < 1e-6  # (the float mean agrees to rounding)
     clpt.lib().CLResetAccumulation()
     renderer.execute()
     one = renderer.read_image()
-    ref = oracle.render(scene, cam, 160, 120, mode=1, depth=2, spp=2, seed=3, flags=clpt.FLAG_JITTER)
+    ref = oracle.render(scene, cam, 160, 120, mode=1, depth=2, spp=2, seed=3, flags=flags, aov=False)
     _assert_bit_equal(one, ref["rgba"], "after reset")
     renderer.set_params()
 
@@ -572,32 +577,28 @@ def test_readback_formats_and_pipeline(clpt, oracle, renderer, scene_cache):
     # progressive: the RGBA8 read-back is the normalised running mean
     renderer.set_params(mode=1, depth=3, spp=1, seed=4, flags=clpt.FLAG_JITTER | clpt.FLAG_ACCUMULATE)
     renderer.create_image(w, h)
-    acc = np.zeros((h, w, 4), dtype=np.float32)
+    acc = oracle.new_accumulator(w, h)
     for base in range(3):
         renderer.execute()
-        oracle.render(scene, cam, w, h, mode=1, depth=3, spp=1, seed=4, aov=False, sample_base=base,
-                      flags=oracle.FLAG_JITTER | oracle.FLAG_ACCUMULATE, accumulate_into=acc)
-    mean = np.ones_like(acc)
-    mean[..., :3] = acc[..., :3] * (np.float32(1.0) / acc[..., 3:4])
+        mean = oracle.render(scene, cam, w, h, mode=1, depth=3, spp=1, seed=4, aov=False, sample_base=base,
+                             flags=oracle.FLAG_JITTER | oracle.FLAG_ACCUMULATE, accumulate_into=acc)["rgba"]
     _assert_bit_equal(renderer.read_image(), mean, "progressive float4")
     assert np.array_equal(renderer.read_image_rgba8(), _unorm8(mean))
     renderer.set_params(mode=0, depth=2)
 
 
-def test_progressive_sharded_accumulates_locally(clpt, oracle, renderer, scene_cache):
-    """Progressive accumulation under row-tile sharding: a rank sums its
-    own rows in its slab, frame after frame, and the rows are placed only on read-back."""
+def test_progressive_sharded_by_sample(clpt, oracle, renderer, scene_cache):
+    """Progressive accumulation across ranks is spread by SAMPLE: rank r
+    of N renders the WHOLE frame with samples base + r*spp .. of every round of N*spp samples into
+    its own fixed-point sums; the read-back adds the ranks' sums (here, without a communicator,
+    each rank's own).  The three ranks' sums added together are the single-rank sums of the same
+    eighteen samples, bit for bit."""
     scene, _ = scene_cache("hf22n")
     w, h = 200, 150
     cam = _cam(clpt, "canonical", h)
     L = clpt.lib()
-    acc = np.zeros((h, w, 4), dtype=np.float32)
     kw = dict(mode=1, depth=3, spp=2, seed=6)
-    for base in (0, 2, 4):
-        oracle.render(scene, cam, w, h, aov=False, sample_base=base, accumulate_into=acc,
-                      flags=oracle.FLAG_JITTER | oracle.FLAG_ACCUMULATE, **kw)
-    mean = np.ones_like(acc)
-    mean[..., :3] = acc[..., :3] * (np.float32(1.0) / acc[..., 3:4])
+    oflags = oracle.FLAG_JITTER | oracle.FLAG_ACCUMULATE
     try:
         for rank in range(3):
             renderer.set_meshes(scene)
@@ -605,11 +606,13 @@ def test_progressive_sharded_accumulates_locally(clpt, oracle, renderer, scene_c
             renderer.set_params(flags=clpt.FLAG_JITTER | clpt.FLAG_ACCUMULATE, **kw)
             renderer.create_image(w, h)
             L.CLSetTileShard(rank, 3, 8)
-            for _ in range(3):
+            acc = oracle.new_accumulator(w, h)
+            for frame in range(3):
                 renderer.execute()
-            rows = np.array([y for y in range(h) if (y // 8) % 3 == rank], dtype=int)
-            _assert_bit_equal(renderer.read_image()[rows], mean[rows], f"rank {rank}")
-            assert np.array_equal(renderer.read_image_rgba8()[rows], _unorm8(mean)[rows])
+                mean = oracle.render(scene, cam, w, h, aov=False, sample_base=frame * 6 + rank * 2, accumulate_into=acc,
+                                     flags=oflags, **kw)["rgba"]
+            _assert_bit_equal(renderer.read_image(), mean, f"rank {rank}")
+            assert np.array_equal(renderer.read_image_rgba8(), _unorm8(mean))
     finally:
         L.CLSetTileShard(0, 1, 8)
         renderer.set_params(mode=0, depth=2)
@@ -633,21 +636,17 @@ def test_band_parity_10m(clpt, oracle, renderer):
     ref = oracle.render(scene, cam, w, h, rows=band, aov=False, flags=oracle.FLAG_JITTER, **kw)
     _assert_bit_equal(img[sl], ref["rgba"][sl], "10M triangles, 4K, depth 5")
     assert (img[..., :3] != 1.0).any(axis=-1).mean() > 0.2  # the camera sees the terrain
-    # progressive: two 1-spp frames accumulate to the oracle's two-frame sum, normalised on readback
+    # progressive: two 1-spp frames accumulate to the oracle's two-frame sums; the read-back is the mean
     renderer.set_params(flags=clpt.FLAG_JITTER | clpt.FLAG_ACCUMULATE, **kw)
     renderer.create_image(w, h)
     renderer.execute()
     renderer.execute()
     got = renderer.read_image()
-    acc = np.zeros((h, w, 4), dtype=np.float32)
+    acc = oracle.new_accumulator(w, h)
     for base in (0, 1):
-        oracle.render(scene, cam, w, h, rows=band, aov=False, flags=oracle.FLAG_JITTER | oracle.FLAG_ACCUMULATE,
-                      sample_base=base, accumulate_into=acc, **kw)
-    want = np.zeros_like(acc[sl])
-    k = np.float32(1.0) / acc[sl][..., 3:4]
-    want[..., :3] = acc[sl][..., :3] * k
-    want[..., 3] = 1.0
-    _assert_bit_equal(got[sl], want, "two accumulated frames")
+        want = oracle.render(scene, cam, w, h, rows=band, aov=False, flags=oracle.FLAG_JITTER | oracle.FLAG_ACCUMULATE,
+                             sample_base=base, accumulate_into=acc, **kw)["rgba"]
+    _assert_bit_equal(got[sl], want[sl], "two accumulated frames")
     renderer.set_params(mode=0, depth=2)
 
 

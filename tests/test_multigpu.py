@@ -62,17 +62,15 @@ for tile_rows, engine, direct in ((8, 1, 1), (4, 1, 1), (8, 2, 1), (8, 1, 0)):
         print(f"rank {rank} tile_rows {tile_rows} engine {engine} direct {got_direct} seed {seed}: "
               f"{'ok' if same else 'MISMATCH'}", flush=True)
         ok = ok and same
-    # progressive: every rank accumulates its own rows, nothing crosses GPUs per frame; the
-    # (collective) read-back gathers and normalises.  RGBA8 is the reference's texture format.
+    # progressive: spread by SAMPLE -- every rank renders the whole frame with its own sample indices into
+    # its own fixed-point sums, nothing crosses GPUs per frame; the (collective) read-back adds the ranks'
+    # sums and normalises.  Three frames of 2 spp on `world` ranks = samples 0 .. 6*world-1.
     r.set_params(mode=1, depth=4, spp=2, seed=9, flags=cl.FLAG_JITTER | cl.FLAG_ACCUMULATE)
     r.create_image(w, h)
-    acc = np.zeros((h, w, 4), dtype=np.float32)
-    for base in (0, 2, 4):
+    for _ in range(3):
         r.execute()
-        op.render(scene, cam, w, h, mode=1, depth=4, spp=2, seed=9, aov=False, sample_base=base, accumulate_into=acc,
-                  flags=op.FLAG_JITTER | op.FLAG_ACCUMULATE)
-    mean = np.ones_like(acc)
-    mean[..., :3] = acc[..., :3] * (np.float32(1.0) / acc[..., 3:4])
+    mean = op.render(scene, cam, w, h, mode=1, depth=4, spp=6 * world, seed=9, aov=False,
+                     flags=op.FLAG_JITTER | op.FLAG_ACCUMULATE)["rgba"]
     q = np.rint(np.clip(mean, 0.0, 1.0).astype(np.float32) * np.float32(255.0)).astype(np.uint8)
     same = np.array_equal(r.read_image().view(np.uint32), mean.view(np.uint32)) and \
         np.array_equal(r.read_image_rgba8(), q)
