@@ -26,7 +26,13 @@ import threading
 import time
 from pathlib import Path
 
-import numpy as np
+# torchrun exports OMP_NUM_THREADS=1.  The (untimed) host kd build of every rank should still use the
+# rank's share of the host cores -- 10M triangles on one thread take over a minute -- and libgomp reads
+# the variable when it is first loaded, so it is corrected here, before anything that links it is imported.
+if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("OMP_NUM_THREADS") == "1":
+    os.environ["OMP_NUM_THREADS"] = str(max(1, len(os.sched_getaffinity(0)) // int(os.environ["WORLD_SIZE"])))
+
+import numpy as np  # noqa: E402
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
@@ -707,6 +713,9 @@ def main():
             baseline, parity = None, {"checked": False}
         # every rank holds the whole frame: one sha per rank, to be compared with each other and,
         # across runs, with the N=1 line's
+        if a.progressive:
+            parity["check_frame"] = (f"the first progressive frame after a reset: the mean of ranks x spp = "
+                                     f"{world * a.spp} samples per pixel (the oracle adds the same samples)")
         parity["frame_sha256"] = shas[0]
         parity["frame_sha256_per_rank"] = shas
         parity["ranks_agree"] = len(set(shas)) == 1
