@@ -461,6 +461,23 @@ def run_animated(a):
         if f >= a.warmup:
             t_build.append(t1 - t0), t_upload.append(t2 - t1), t_render.append(t3 - t2), t_frame.append(t3 - t0)
     gc.enable()
+    # self-check: the LAST frame (whatever tree the last rebuild made) against the oracle walking that tree
+    parity = {"checked": False}
+    if not a.no_parity_check:
+        import hashlib
+
+        from oracle import oracle_py as op
+
+        frame = r.read_image()
+        sha = hashlib.sha256(frame.tobytes()).hexdigest()
+        if rank == 0:
+            tree = r.download_kd() if a.anim_builder == "gpu" else scene
+            ref = op.render(tree, cam, a.width, a.height, mode=1, depth=a.depth, spp=a.spp, seed=a.seed,
+                            flags=op.FLAG_JITTER, aov=False, threads=host_cores())["rgba"]
+            differ = int(np.count_nonzero(frame.view(np.uint32) != ref.view(np.uint32)))
+            parity = {"checked": True, "words_differ": differ, "words": int(ref.size), "frame_sha256": sha,
+                      "oracle": "oracle/oracle_kernel.c walking the tree of the last frame"
+                                + (" (downloaded from the device, CLDownloadKd)" if a.anim_builder == "gpu" else "")}
     L.PhysTerminate()
     if world > 1:
         L.CLDistShutdown()
@@ -478,6 +495,7 @@ def run_animated(a):
               "value": ms(t_frame, 50), "unit": "ms", "higher_is_better": False, "n_gpus": world, "steps": len(t_frame),
               "warmup": a.warmup, "p50_ms": ms(t_frame, 50), "p99_ms": ms(t_frame, 99), "max_ms": ms(t_frame, 100),
               "breakdown_p50_ms": breakdown, "kd_builder": "device (CLBuildMeshes)" if gpu else "host (build_kd_sah, binned)",
+              "parity": parity,
               "config": dict(workload_config(a), triangles=int(len(corners) // 3)), "data": "synthetic", "dtype": "f32"})
     if world > 1:
         dist.destroy_process_group()

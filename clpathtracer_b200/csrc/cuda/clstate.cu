@@ -725,7 +725,10 @@ void clpt_state_launch_frame(int width, int height) {
         F.row_cost = St.row_cost.ptr;
         if (St.claim_reverse) F.flags |= CLPT_F_REVERSE;
     }
-    if (p2p) flag_barrier(); // every rank has finished with (reading) the previous frame
+    if (p2p) {
+        flag_barrier(); // every rank has finished with (reading) the previous frame
+        St.last_launches++;
+    }
     CU(cudaEventRecord(St.ev_start, St.stream));
     clpt_launch_render(St.scene, F, St.prop.multiProcessorCount, St.stream);
     St.last_launches++;
@@ -738,6 +741,7 @@ void clpt_state_launch_frame(int width, int height) {
 
     if (p2p) {
         flag_barrier(); // every rank's pixels have landed in this rank's frame
+        St.last_launches++;
     } else if (local_only) {
         // this rank's samples went into its own sums; CLReadImage* adds the ranks' buffers (displayable_frame)
     } else if (St.nranks > 1 && St.comm) {

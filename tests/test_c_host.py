@@ -10,10 +10,11 @@ import pytest
 ROOT = Path(__file__).resolve().parents[1]
 
 
-def _build(tmp_path, clpt):
-    exe = tmp_path / "headless_host"
-    cmd = ["gcc", "-std=c11", "-I" + str(ROOT / "include"), str(ROOT / "examples" / "headless_host.c"),
-           "-L" + str(clpt.LIB_PATH.parent), "-lclpt", "-Wl,-rpath," + str(clpt.LIB_PATH.parent), "-lm", "-o", str(exe)]
+def _build(tmp_path, clpt, name="headless_host", extra=()):
+    exe = tmp_path / name
+    cmd = ["gcc", "-std=c11", "-I" + str(ROOT / "include"), str(ROOT / "examples" / (name + ".c")),
+           "-L" + str(clpt.LIB_PATH.parent), "-lclpt", "-Wl,-rpath," + str(clpt.LIB_PATH.parent), "-lm", *extra,
+           "-o", str(exe)]
     subprocess.run(cmd, check=True, capture_output=True)
     return exe
 
@@ -44,3 +45,36 @@ def test_c_host_renders(clpt, oracle, tmp_path):
     ref = oracle.render(scene, cam, 160, 120, mode=1, depth=2)["rgba"][..., :3]
     want = (np.clip(ref, 0, 1) * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)
     assert np.array_equal(img, want)
+
+
+def test_gl_host_compiles_and_links(clpt, tmp_path):
+    """examples/egl_present.c (the stand-in for GLHandler.c on a headless box) builds against the ABI."""
+    _build(tmp_path, clpt, "egl_present", ("-ldl",))
+
+
+@pytest.mark.gpu
+def test_gl_presentation_hook(clpt, tmp_path):
+    """CLCreateImage(GLuint) + CLExecute present the frame into a real RGBA8 GL texture
+    (src/CLState.c:47-63,204-219): a surfaceless OpenGL context is made through NVIDIA's EGL
+    vendor library, the texture is read back with glGetTexImage and must equal
+    CLReadImageRGBA8 byte for byte.  Skips (with the program's diagnosis) where no GL context
+    can be had."""
+    from clpathtracer_b200 import scenes
+
+    exe = _build(tmp_path, clpt, "egl_present", ("-ldl",))
+    v, c, n = scenes.heightfield(22, True)
+    obj = tmp_path / "hf22.obj"
+    scenes.write_obj_text(str(obj), v, c, n)
+    out = subprocess.run([str(exe), "320", "240", str(obj)], capture_output=True, text=True, timeout=120)
+    print(out.stdout[-2000:], out.stderr[-2000:])
+    log = ROOT / "gpurun_out"
+    if log.is_dir():
+        (log / "egl_present.txt").write_text(f"exit {out.returncode}\n{out.stdout}\n{out.stderr}")
+    if out.returncode == 77:
+        pytest.skip("no usable EGL/OpenGL context here: " + out.stdout.strip().splitlines()[-1])
+    if out.returncode < 0 and "CONTEXT:" not in out.stdout:
+        # died inside the vendor library before a context existed: the hand-declared libglvnd vendor
+        # ABI did not match this driver -- nothing of ours has run yet
+        pytest.skip(f"the EGL vendor library could not be driven without libglvnd (signal {-out.returncode})")
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    assert "PRESENTED" in out.stdout

@@ -154,3 +154,32 @@ def test_leaf_visit_cap(clpt, oracle, scene_cache):
     capped = oracle.render(scene, cam, 80, 60, mode=0, depth=2, max_leaf_visits=2)
     assert capped["counters"]["capped"] > 0
     assert capped["counters"]["leaves"] < free["counters"]["leaves"]
+
+
+def test_progressive_sums_do_not_depend_on_the_grouping(clpt, oracle):
+    """Progressive accumulation is 2^-32 fixed point (oracle_kernel.c: fix32): integer sums, so
+    twelve samples added as 12, as 4 x 3 in order, or as three interleaved streams of every third
+    sample (how N GPUs split them) give the same words -- and the mean agrees with the float mean
+    of a plain 12-spp frame to rounding."""
+    from clpathtracer_b200 import scenes
+
+    scene = clpt.build_kd(*scenes.heightfield(22, True))
+    w, h = 96, 64
+    cam = clpt.cam_matrix(clpt.make_camera(**scenes.CANONICAL_CAMERA), h)
+    kw = dict(mode=1, depth=3, seed=8, aov=False)
+    fl = oracle.FLAG_JITTER | oracle.FLAG_ACCUMULATE
+    once = oracle.render(scene, cam, w, h, spp=12, flags=fl, **kw)
+    acc = oracle.new_accumulator(w, h)
+    for base in (0, 3, 6, 9):
+        seq = oracle.render(scene, cam, w, h, spp=3, sample_base=base, flags=fl, accumulate_into=acc, **kw)
+    assert np.array_equal(acc, once["accum"]) and np.array_equal(seq["rgba"].view(np.uint32), once["rgba"].view(np.uint32))
+    ranks = [oracle.new_accumulator(w, h) for _ in range(3)]
+    for frame in range(4):               # frame k: rank r adds sample 3k + r
+        for r in range(3):
+            oracle.render(scene, cam, w, h, spp=1, sample_base=3 * frame + r, flags=fl, accumulate_into=ranks[r], **kw)
+    assert np.array_equal(ranks[0] + ranks[1] + ranks[2], once["accum"])
+    assert np.all(once["accum"][..., 3] == 12)
+    plain = oracle.render(scene, cam, w, h, spp=12, flags=oracle.FLAG_JITTER, **kw)["rgba"]
+    assert np.abs(plain - once["rgba"]).max() < 1e-6
+    # quantisation: a colour of exactly 1.0 is 2^32 units, white stays white
+    assert np.all(once["rgba"][..., :3] <= 1.0) and once["rgba"][..., 3].min() == 1.0
