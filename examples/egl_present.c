@@ -176,15 +176,24 @@ int main(int argc, char **argv) {
 
     EGLDeviceEXT devs[16];
     EGLint ndev = 0;
-    if (!eglQueryDevicesEXT(16, devs, &ndev) || ndev < 1) return skip("eglQueryDevicesEXT found no device");
-    printf("%d EGL device(s)\n", ndev);
     EGLDisplay dpy = NULL;
     EGLint major = 0, minor = 0;
-    for (int d = 0; d < ndev && !dpy; d++) {
+    const EGLBoolean q = eglQueryDevicesEXT(16, devs, &ndev);
+    printf("eglQueryDevicesEXT: returned %u, %d device(s), EGL error 0x%x\n", q, ndev, (unsigned)g_err);
+    for (int d = 0; q && d < ndev && !dpy; d++) {
         EGLDisplay cand = im.getPlatformDisplay(EGL_PLATFORM_DEVICE_EXT, devs[d], NULL);
         if (cand && eglInitialize(cand, &major, &minor)) dpy = cand;
     }
-    if (!dpy) return skip("eglInitialize failed on every device");
+    if (!dpy) { /* no device enumerated (a compute-only container?): the surfaceless platform, then the default display */
+        const EGLenum platforms[] = { 0x31DD /* EGL_PLATFORM_SURFACELESS_MESA */, EGL_PLATFORM_DEVICE_EXT };
+        for (int k = 0; k < 2 && !dpy; k++) {
+            EGLDisplay cand = im.getPlatformDisplay(platforms[k], NULL, NULL);
+            printf("getPlatformDisplay(0x%x, default): %p, EGL error 0x%x\n", platforms[k], cand, (unsigned)g_err);
+            if (cand && eglInitialize(cand, &major, &minor)) dpy = cand;
+            else if (cand) printf("  eglInitialize failed, EGL error 0x%x\n", (unsigned)g_err);
+        }
+    }
+    if (!dpy) return skip("no EGL display could be initialised (no device enumerated: the container exposes the GPU for compute only)");
     printf("EGL %d.%d, vendor %s\n", major, minor, eglQueryString(dpy, EGL_VENDOR));
     if (!eglBindAPI(EGL_OPENGL_API)) return skip("eglBindAPI(EGL_OPENGL_API) failed");
     g_api = EGL_OPENGL_API;
