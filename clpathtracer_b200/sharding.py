@@ -14,6 +14,14 @@ from __future__ import annotations
 import numpy as np
 
 
+def first_sample_of_rank(frame: int, rank: int, nranks: int, spp: int) -> int:
+    """Progressive frames (CLPT_FLAG_ACCUMULATE) are spread over ranks by SAMPLE, not by region:
+    frame k on N ranks adds samples [k*N*spp, (k+1)*N*spp) of every pixel, of which rank r
+    renders [k*N*spp + r*spp, ... + spp) -- the whole frame -- into its own fixed-point sums;
+    a read-back adds the ranks' sums (clstate.cu: clpt_state_launch_frame / displayable_frame)."""
+    return (frame * nranks + rank) * spp
+
+
 def slab_rows(height: int, nranks: int, tile_rows: int) -> int:
     tiles = -(-height // tile_rows)
     return -(-tiles // nranks) * tile_rows

@@ -51,6 +51,45 @@ def _worker(rank, world, port, tile_rows, out_dir):
     dist.destroy_process_group()
 
 
+def _progressive_worker(rank, world, port, out_dir):
+    """Progressive frames spread by sample: every rank adds its samples of three frames to its own
+    fixed-point sums (the oracle standing in for the device), an all-reduce adds the ranks' sums."""
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, str(ROOT))
+    import clpathtracer_b200 as cl
+    from clpathtracer_b200 import scenes, sharding
+    from oracle import oracle_py as op
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    w, h, spp, frames = 48, 32, 2, 3
+    scene = cl.build_kd(*scenes.heightfield(22, True))
+    cam = cl.cam_matrix(cl.make_camera(**scenes.CANONICAL_CAMERA), h)
+    kw = dict(mode=1, depth=3, seed=4, aov=False, threads=1, flags=op.FLAG_JITTER | op.FLAG_ACCUMULATE)
+    acc = op.new_accumulator(w, h)
+    for k in range(frames):
+        op.render(scene, cam, w, h, spp=spp, sample_base=sharding.first_sample_of_rank(k, rank, world, spp),
+                  accumulate_into=acc, **kw)
+    total = torch.from_numpy(acc.view(np.int64).copy())   # (gloo has no uint64; the sums are far below 2^63)
+    dist.all_reduce(total)
+    if rank == 0:
+        one = op.render(scene, cam, w, h, spp=spp * world * frames, **kw)
+        np.save(Path(out_dir) / "ok.npy", np.array([np.array_equal(total.numpy().view(np.uint64), one["accum"])]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_progressive_by_sample(tmp_path, world, clpt, oracle):
+    import torch.multiprocessing as mp
+
+    port = _free_port()
+    mp.spawn(_progressive_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert np.load(tmp_path / "ok.npy")[0]
+
+
 @pytest.mark.parametrize("world,tile_rows", [(2, 8), (3, 4)])
 def test_gloo_row_tile_gather(tmp_path, world, tile_rows, clpt, oracle):
     import torch.multiprocessing as mp
