@@ -206,6 +206,62 @@ __device__ __forceinline__ void triangle_run(const float4 *__restrict__ tri, int
     }
 }
 
+// ---- several lanes per ray (engine 2, one sample per pixel) -------------------------------
+// On a reference-built tree a leaf holds ~56 triangles and a grazing ray tests thousands; with one
+// lane per ray a frame ends on a handful of warps walking such rays (ncu: 47% of the warp slots
+// occupied on average).  Here K = 4 neighbouring lanes walk the SAME ray -- the descent and the
+// leaf steps are done redundantly (a few percent of the work, identical control flow, broadcast
+// loads) -- and share a leaf's triangle run: lane j tests triangles j, j+K, j+2K, ...  A warp tile
+// is then 8 pixels instead of 32: four times as many claims, each a quarter as long.
+// Combining the K partial results reproduces the serial loop exactly: the smallest t wins; among
+// equal t a triangle accepted in THIS leaf beats the hit carried in from earlier leaves
+// (`t <= minHit`, src/kernel.cl:344) and the later triangle beats the earlier.
+template <bool COUNT>
+__device__ __forceinline__ void triangle_run_shared(const float4 *__restrict__ tri, int first, int count, int sub,
+                                                    int log2_k, V3 o, V3 d, int &ref, float &min_hit, Counters &cn) {
+    bool changed = false;
+    for (int i = first + sub; i < first + count; i += 1 << log2_k) {
+        const float4 b = __ldg(tri + 3 * (size_t)i + 1);
+        const float4 c = __ldg(tri + 3 * (size_t)i + 2);
+        if (COUNT) cn.tris++;
+        const V3 e1 = xyz(b), e2 = xyz(c);
+        const V3 pvec = vcross(d, e2);
+        const float det = vdot(e1, pvec);
+        if (det < 0.0f) continue;
+        const float4 a = __ldg(tri + 3 * (size_t)i);
+        const float idet = frcp(det);
+        const V3 tvec = vsub(o, xyz(a));
+        const float u = fmul(vdot(tvec, pvec), idet);
+        if (u < 0.0f || u > 1.0f) continue;
+        const V3 qvec = vcross(tvec, e1);
+        const float v = fmul(vdot(d, qvec), idet);
+        if (v < 0.0f || fadd(u, v) > 1.0f) continue;
+        const float t = fmul(vdot(e2, qvec), idet);
+        if (!(t > 0.0f)) continue;
+        if (ref < 0 || t <= min_hit) {
+            min_hit = t;
+            ref = i;
+            changed = true;
+        }
+    }
+    // combine over the K lanes of the ray (they are converged: same ray, same control flow)
+    const int lane = threadIdx.x & 31;
+    const unsigned mask = ((1u << (1 << log2_k)) - 1u) << (lane & ~((1 << log2_k) - 1));
+    float t = ref >= 0 ? min_hit : __int_as_float(0x7f800000);
+    int pri = changed ? ref : -1, r = ref;
+    for (int off = 1; off < (1 << log2_k); off <<= 1) {
+        const float ot = __shfl_xor_sync(mask, t, off);
+        const int opri = __shfl_xor_sync(mask, pri, off), orf = __shfl_xor_sync(mask, r, off);
+        if (ot < t || (ot == t && opri > pri)) {
+            t = ot;
+            pri = opri;
+            r = orf;
+        }
+    }
+    ref = r;
+    if (r >= 0) min_hit = t;
+}
+
 // Early-out after a leaf: 0.001 is a double literal in the reference (:381).
 __device__ __forceinline__ bool hit_is_final(int ref, float tmin, float min_hit) {
     return ref >= 0 && (double)tmin + 0.001 > (double)min_hit;
@@ -228,13 +284,16 @@ __device__ __forceinline__ bool leave_leaf(const uint2 *__restrict__ nodes, cons
     return false;
 }
 
-// Traversal of one ray to completion.
-template <bool COUNT>
-__device__ __forceinline__ Hit closest_hit(const ClptScene &S, V3 o, V3 d, int max_visits,
-                                           Counters &cn) {
+// Traversal of one ray to completion.  SHARE: 1 << log2_k neighbouring lanes walk this same ray
+// and split the triangle runs (lane `sub` of them; only sub 0 counts the per-ray work).
+template <bool COUNT, bool SHARE = false>
+__device__ __forceinline__ Hit closest_hit(const ClptScene &S, V3 o, V3 d, int max_visits, Counters &cn_in,
+                                           int sub = 0, int log2_k = 0) {
     Hit h;
     h.ref = -1;
     h.t = 0.0f;
+    Counters scratch = { 0, 0, 0, 0, 0, 0 };
+    Counters &cn = (SHARE && sub != 0) ? scratch : cn_in; // (the helpers' visits are not the algorithm's)
     if (COUNT) cn.rays++;
     const V3 inv = mk(frcp(d.x), frcp(d.y), frcp(d.z));
     float tmin, tmax;
@@ -261,7 +320,12 @@ __device__ __forceinline__ Hit closest_hit(const ClptScene &S, V3 o, V3 d, int m
         // was measured too: -8%.  profiles/r01_experiments.json)
         int far;
         leaf_exit(lmin, lmax, o, inv, tmax, far);
-        triangle_run<COUNT>(S.tri, __float_as_int(lmin.w), __float_as_int(lmax.w), o, d, h.ref, min_hit, cn);
+        if (SHARE) {
+            triangle_run_shared<COUNT>(S.tri, __float_as_int(lmin.w), __float_as_int(lmax.w), sub, log2_k, o, d, h.ref,
+                                       min_hit, cn_in);
+        } else {
+            triangle_run<COUNT>(S.tri, __float_as_int(lmin.w), __float_as_int(lmax.w), o, d, h.ref, min_hit, cn);
+        }
         // (the box is re-read from L1 rather than kept live across the run)
         if (h.ref >= 0 && hit_is_final(h.ref, leaf_entry(__ldg(L), __ldg(L + 1), o, inv), min_hit)) break;
         if (leave_leaf<COUNT>(nodes, L, far, o, d, tmax, max_visits, p1, n, visits, cn)) break;

@@ -39,15 +39,17 @@ __host__ __device__ inline void warp_tile_dims(int log2_ppw, int &tw, int &th) {
     th = 1 << (log2_ppw >> 1);
 }
 
-template <int MODE, bool COUNT>
+template <int MODE, bool COUNT, bool SHARE>
 __device__ __forceinline__ V3 trace_sample(const ClptScene &S, const ClptFrame &F, int x, int y, unsigned pixel,
-                                           unsigned sample, bool aov, Counters &cn) {
+                                           unsigned sample, bool aov, Counters &cn_in, int sub, int log2_k) {
+    Counters scratch = { 0, 0, 0, 0, 0, 0 };
+    Counters &cn = (SHARE && sub != 0) ? scratch : cn_in; // shading is counted once per ray
     V3 o, d;
     primary_ray(F, x, y, pixel, sample, o, d);
     if (MODE == 2) {
         V3 Lsum = mk(0.0f, 0.0f, 0.0f), T = mk(1.0f, 1.0f, 1.0f);
         for (int seg = 0; seg < F.depth; seg++) {
-            const Hit h = closest_hit<COUNT>(S, o, d, F.max_leaf_visits, cn);
+            const Hit h = closest_hit<COUNT, SHARE>(S, o, d, F.max_leaf_visits, cn_in, sub, log2_k);
             if (seg == 0 && aov) write_aov<COUNT>(S, F, h, o, d, x, y);
             if (h.ref < 0) {
                 Lsum = vadd(Lsum, T);
@@ -85,7 +87,7 @@ __device__ __forceinline__ V3 trace_sample(const ClptScene &S, const ClptFrame &
     if (MODE == 0) depth = depth > 0 ? 1 : 0;
     const int first_depth = depth;
     for (; depth > 0; depth--) {
-        const Hit h = closest_hit<COUNT>(S, o, d, F.max_leaf_visits, cn);
+        const Hit h = closest_hit<COUNT, SHARE>(S, o, d, F.max_leaf_visits, cn_in, sub, log2_k);
         if (depth == first_depth && aov) write_aov<COUNT>(S, F, h, o, d, x, y);
         if (h.ref < 0) break;
         const V3 nrm = hit_normal<COUNT>(S, h, o, d, cn);
@@ -138,9 +140,13 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
     // rows; the group's first warp does the ordered sum.  G = 1 is the plain scheme.
     const int log2_g = F.log2_warps_per_pixel, g_warps = 1 << log2_g;
     const int group = warp >> log2_g, member = warp & (g_warps - 1);
+    // Lanes per ray (engine 2 at one sample per pixel only, clpt_trace.cuh: triangle_run_shared):
+    // 1 << log2_r neighbouring lanes walk the same ray, a warp tile is 32 >> log2_r pixels.
+    const int log2_r = VARIANT == 1 ? F.log2_lanes_per_ray : 0;
+    const int sub = lane & ((1 << log2_r) - 1);
     int tw, th;
-    warp_tile_dims(5 - log2_s, tw, th);
-    const int pslot = lane >> log2_s, sslot = lane & (s_lanes - 1);
+    warp_tile_dims(5 - log2_s - log2_r, tw, th);
+    const int pslot = lane >> (log2_s + log2_r), sslot = (lane >> log2_r) & (s_lanes - 1);
     const int spp = F.spp < 1 ? 1 : F.spp;
     const int group_base = lane & ~(s_lanes - 1);
     Counters cn = { 0, 0, 0, 0, 0, 0 };
@@ -202,7 +208,7 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
         for (int base = 0; base < spp; base += round_samples) {
             const int s = base + (member << log2_s) + sslot; // (member > 0 only when s_lanes == 32)
             V3 colour = mk(0.0f, 0.0f, 0.0f);
-            if (valid && s == 0 && F.aov_prim != nullptr && F.depth <= 0) {
+            if (valid && s == 0 && sub == 0 && F.aov_prim != nullptr && F.depth <= 0) {
                 // nothing is traced: the AOVs say "miss" instead of keeping the previous frame's
                 Hit none;
                 none.ref = -1;
@@ -211,8 +217,9 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
             }
             const int in_round = min(round_samples, spp - base);
             if (valid && s < spp) {
-                colour = trace_sample<MODE, COUNT>(S, F, x, y, pixel, F.sample_base + (unsigned)s,
-                                                   s == 0 && F.aov_prim != nullptr, cn);
+                colour = trace_sample<MODE, COUNT, VARIANT == 1>(S, F, x, y, pixel, F.sample_base + (unsigned)s,
+                                                                 s == 0 && sub == 0 && F.aov_prim != nullptr, cn, sub,
+                                                                 log2_r);
             }
             my_stage[0 * row_len + my_col] = colour.x;
             my_stage[1 * row_len + my_col] = colour.y;
@@ -257,7 +264,7 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
                     acc = mk(r, g, bl);
                 }
             }
-            if (valid && sslot == 0) {
+            if (valid && sslot == 0 && sub == 0) {
                 if (accumulate) accumulate_pixel(F, x, y, fx, fy, fz, spp);
                 else store_pixel(F, x, ly, acc, spp);
             }
@@ -357,15 +364,16 @@ void launch_mode(const ClptScene &scene, const ClptFrame &frame, unsigned grid, 
 
 int clpt_render_block_rows(const ClptFrame &frame) {
     int tw, th;
-    warp_tile_dims(5 - frame.log2_sample_lanes, tw, th);
+    warp_tile_dims(5 - frame.log2_sample_lanes - ((frame.flags & CLPT_F_FAT) ? frame.log2_lanes_per_ray : 0), tw, th);
     const int block_h = 2 * th;
     return (frame.local_rows + block_h - 1) / block_h;
 }
 
 void clpt_launch_render(const ClptScene &scene, const ClptFrame &frame_in, int sm_count, cudaStream_t stream) {
     ClptFrame frame = frame_in;
+    if (!(frame.flags & CLPT_F_FAT)) frame.log2_lanes_per_ray = 0;
     int tw, th;
-    warp_tile_dims(5 - frame.log2_sample_lanes, tw, th);
+    warp_tile_dims(5 - frame.log2_sample_lanes - frame.log2_lanes_per_ray, tw, th);
     const int block_w = 4 * tw, block_h = 2 * th;
     const unsigned bx = (unsigned)((frame.width + block_w - 1) / block_w);
     const unsigned by = (unsigned)((frame.local_rows + block_h - 1) / block_h);
