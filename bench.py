@@ -692,7 +692,9 @@ def main():
         out = {
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            # by region the frame is fixed as N grows (strong); progressive frames are spread by sample:
+            # every rank renders a whole frame per step, the step's sample count grows with N (weak)
+            "scaling": "weak" if a.progressive else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(a),
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": 64,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": round(e2e_ms / a.steps, 4),

@@ -69,7 +69,7 @@ struct ClptFrame {
     int log2_sample_lanes;       // lanes per pixel = 1 << this (largest power of two <= min(spp, 32))
     int log2_warps_per_pixel;    // warps of a block sharing one pixel's samples (> 0 only at >= 64 spp)
     int log2_lanes_per_ray;      // engine 2 at 1 spp: neighbouring lanes that walk the same ray and share its
-                                 // leaves' triangle runs (0 or 2); a warp tile is then 32 >> this pixels
+                                 // leaves' triangle runs (0 or 1); a warp tile is then 32 >> this pixels
     unsigned int seed, sample_base;
     int max_leaf_visits;
     int rank, nranks, tile_rows; // row-tile sharding; nranks == 1 -> whole image

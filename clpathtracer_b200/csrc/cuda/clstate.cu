@@ -697,8 +697,8 @@ void clpt_state_launch_frame(int width, int height) {
     // leaves, render_kernel.cu); 0 = chosen from the tree at CLSetMeshes.
     St.last_engine = St.engine != 0 ? St.engine : St.auto_engine;
     if (St.last_engine == 2) F.flags |= CLPT_F_FAT;
-    // engine 2, one sample per pixel: four lanes per ray (clpt_trace.cuh: triangle_run_shared)
-    F.log2_lanes_per_ray = (St.last_engine == 2 && F.log2_sample_lanes == 0) ? 2 : 0;
+    // engine 2, one sample per pixel: two lanes per ray (clpt_trace.cuh: triangle_run_shared)
+    F.log2_lanes_per_ray = (St.last_engine == 2 && F.log2_sample_lanes == 0) ? 1 : 0;
     if (const char *e = getenv("CLPT_LANES_PER_RAY")) { // measurement only: 1, 2 or 4
         if (St.last_engine == 2 && F.log2_sample_lanes == 0) F.log2_lanes_per_ray = atoi(e) >= 4 ? 2 : (atoi(e) >= 2 ? 1 : 0);
     }
