@@ -11,10 +11,24 @@ synthetic heightfield, canonical camera.  A "step" is one
 frame.  Rays = entries into the traversal loop (src/kernel.cl:311), counted on
 the device by an instrumented frame before timing.
 
-One JSON line on stdout (rank 0).  `value` = Mrays/s with everything resident
-in HBM (device events around CLExecute, max over ranks); `e2e` = the same
-metric through the C ABI with host buffers: camera upload, CLExecute and the
-float4 frame read back to pinned host memory inside the timed region.
+One JSON line on stdout (rank 0).
+  value        Mrays/s with everything resident in HBM (device events around CLExecute, L2 flushed
+               between frames outside the timed events, max over ranks)
+  e2e          the same metric through the C ABI with host buffers: every step uploads the camera
+               matrix, renders, and delivers ONE frame to pinned host memory -- in the reference's
+               render-target format (RGBA8, src/GLHandler.c:177-185) through the pipelined read-back
+               (CLReadImageAsync: frame k travels while frame k+1 renders; all frames have landed
+               before the clock stops); --readback float4 / --readback-sync change that
+  parity       the frame rendered with the timed parameters against the oracle's, word for word,
+               and its sha256 (one per rank at N > 1: every rank holds the whole frame)
+  roofline     the formal HBM bound of SURVEY.md section 8d (algorithmic bytes / kernel time /
+               measured HBM peak) and, in `binding`, what really binds: the utilisation of every
+               unit and the lane-issue efficiency from the ncu capture of the same workload
+               (profiles/binding.json)
+  cpu_baseline the oracle port on all host cores, the full frame at full spp (it is also the
+               parity reference)
+--config c1|c2|c4|c5 run the other BASELINE configs (c4: progressive, spread over GPUs by sample;
+c5: animated, per-frame kd rebuild on the device, reports ms per frame p50/p99).
 """
 from __future__ import annotations
 

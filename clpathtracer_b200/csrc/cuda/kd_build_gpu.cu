@@ -612,18 +612,6 @@ void scan(int n, F f, Triple *out, Triple *total_dev, cudaStream_t s) {
 
 } // namespace
 
-void clpt_gpu_build_release(void) {
-    auto drop = [](auto *&p) {
-        if (p) (void)cudaFree(p);
-        p = nullptr;
-    };
-    drop(W.lo), drop(W.hi), drop(W.ref_tri[0]), drop(W.ref_tri[1]), drop(W.ref_node[0]), drop(W.ref_node[1]);
-    drop(W.nodes[0]), drop(W.nodes[1]), drop(W.dec), drop(W.hist), drop(W.ref_scan), drop(W.node_scan);
-    drop(W.tiles), drop(W.totals), drop(W.box_keys), drop(W.bad);
-    if (W.host_totals) (void)cudaFreeHost(W.host_totals);
-    W = Workspace();
-}
-
 bool clpt_gpu_build(const float4 *verts, int n_verts, const int4 *corners, int n_tris, const ClptGpuBuildParams &P,
                     ClptGpuTree &out, cudaStream_t s, char *err, size_t errlen) {
     if (n_tris <= 0 || n_verts <= 0) {
@@ -936,3 +924,18 @@ bool clpt_gpu_pack(const ClptGpuTree &tree, const float4 *verts, const int4 *cor
     CU(cudaGetLastError());
     return true;
 }
+
+void clpt_gpu_build_release(void) {
+    auto drop = [](auto *&p) {
+        if (p) (void)cudaFree(p);
+        p = nullptr;
+    };
+    drop(W.lo), drop(W.hi), drop(W.ref_tri[0]), drop(W.ref_tri[1]), drop(W.ref_node[0]), drop(W.ref_node[1]);
+    drop(W.nodes[0]), drop(W.nodes[1]), drop(W.dec), drop(W.hist), drop(W.ref_scan), drop(W.node_scan);
+    drop(W.tiles), drop(W.totals), drop(W.box_keys), drop(W.bad);
+    drop(g_new_of), drop(g_wire_scan);
+    g_new_of_cap = g_wire_scan_cap = 0;
+    if (W.host_totals) (void)cudaFreeHost(W.host_totals);
+    W = Workspace();
+}
+
