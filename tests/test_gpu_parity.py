@@ -658,7 +658,14 @@ def test_fails_loudly(clpt):
                          ("L.CLInit(None,None);L.CLExecute(64,64)", "no render target"),
                          ("L.CLInit(None,None);L.CLCreateImageHeadless(8,8);L.CLExecute(8,8)", "no scene"),
                          ("L.CLInit(None,None);L.CLCreateImage(3)", "CUDA Error"),  # no GL context on the box
-                         ("L.CLInit(b'k.cl',b'trace')", "no kernel named")]:
+                         ("L.CLInit(b'k.cl',b'trace')", "no kernel named"),
+                         # the round-2 additions abort the same way
+                         ("L.CLInit(None,None);L.CLCreateImageHeadless(8,8);L.CLReadImageRGBA8(None,7)", "bytes given"),
+                         ("L.CLInit(None,None);L.CLCreateImageHeadless(8,8);L.CLReadImageAsync(None,256,5)", "format must be"),
+                         ("L.CLInit(None,None);L.CLUpdateVertices(0,None,16)", "no mesh was uploaded"),
+                         ("L.CLInit(None,None);L.CLRebuildMeshes()", "no mesh was uploaded"),
+                         ("L.CLInit(None,None);k=cl.KD();L.CLDownloadKd(k)", "not built by CLBuildMeshes"),
+                         ("L.CLInit(None,None);L.CLSetEngine(3)", "CLSetEngine")]:
         p = subprocess.run([sys.executable, "-c", code % (str(root), body)], capture_output=True, text=True)
         assert p.returncode == 1, (body, p.returncode, p.stderr)
         assert needle in p.stderr, (body, p.stderr)
