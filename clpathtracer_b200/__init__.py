@@ -111,6 +111,7 @@ def lib() -> C.CDLL:
         "CLSetMaterials": (None, [vp, sz, vp, sz]),
         "CLBuildMeshes": (None, [vp, sz, vp, sz, vp, sz]), "CLSetBuildParams": (None, [i, i, f, f, f]),
         "CLLastBuildMs": (None, [C.POINTER(f), C.POINTER(f)]), "CLBuildStats": (None, [C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
+        "CLLastBuildWasRecorded": (i, []),
         "CLDownloadKd": (None, [C.POINTER(KD)]), "CLDebugReadPacked": (sz, [i, vp, sz]),
         "CLUpdateVertices": (None, [sz, vp, sz]), "CLRebuildMeshes": (None, []),
         "CLDeleteImage": (None, []), "CLCreateImage": (None, [u]), "CLExecute": (None, [i, i]),
@@ -338,6 +339,10 @@ class Renderer:
         b, p = C.c_float(0), C.c_float(0)
         self.L.CLLastBuildMs(C.byref(b), C.byref(p))
         return b.value, p.value
+
+    def build_was_recorded(self) -> bool:
+        """CLLastBuildWasRecorded: the last device build ran as the recorded graph."""
+        return bool(self.L.CLLastBuildWasRecorded())
 
     def read_packed(self, which: int) -> np.ndarray:
         n = self.L.CLDebugReadPacked(which, None, 0)

@@ -97,7 +97,9 @@ struct ClptFrame {
     // CLPT_F_REVERSE bottom to top.  Every warp tile adds its duration to
     // row_cost[its block row] (null = not recorded); CLExecute looks at where one frame's
     // cost sits and points the next frame's claims so that they END at the cheap side.
+    // row_cost[row_count + block row] keeps the row's LONGEST warp tile (what a frame's tail is made of).
     unsigned long long *row_cost;
+    int row_count;
     int blocks_x, n_warp_tiles;   // filled in by clpt_launch_render
 };
 

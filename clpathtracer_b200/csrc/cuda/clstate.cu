@@ -683,6 +683,7 @@ void clpt_state_launch_frame(int width, int height) {
     F.work_counter = St.work_counter.ptr;
     F.blocks_x = F.n_warp_tiles = 0;
     F.row_cost = nullptr;
+    F.row_count = 0;
     const bool local_only = sample_parallel(); // progressive across GPUs: nothing crosses GPUs per frame
     const bool p2p = St.p2p && St.comm && St.nranks > 1 && !local_only;
     F.n_peer_images = p2p ? St.nranks : 0;
@@ -700,7 +701,11 @@ void clpt_state_launch_frame(int width, int height) {
     // engine 2, one sample per pixel: two lanes per ray (clpt_trace.cuh: triangle_run_shared)
     F.log2_lanes_per_ray = (St.last_engine == 2 && F.log2_sample_lanes == 0) ? 1 : 0;
     if (const char *e = getenv("CLPT_LANES_PER_RAY")) { // measurement only: 1, 2 or 4
-        if (St.last_engine == 2 && F.log2_sample_lanes == 0) F.log2_lanes_per_ray = atoi(e) >= 4 ? 2 : (atoi(e) >= 2 ? 1 : 0);
+        if (St.last_engine == 2 && F.log2_sample_lanes == 0) {
+            int k = atoi(e), lg = 0;
+            while ((2 << lg) <= k && lg < 5) lg++;
+            F.log2_lanes_per_ray = lg;
+        }
     }
 
     // Claim direction (megakernel): decided from the previous frame's per-row cost under
@@ -722,12 +727,13 @@ void clpt_state_launch_frame(int width, int height) {
         }
         if (order_rows > St.row_capacity) {
             if (St.host_row_cost) CU(cudaFreeHost(St.host_row_cost));
-            CU(cudaMallocHost((void **)&St.host_row_cost, (size_t)order_rows * sizeof(unsigned long long)));
-            St.row_cost.resize((size_t)order_rows);
+            CU(cudaMallocHost((void **)&St.host_row_cost, (size_t)2 * order_rows * sizeof(unsigned long long)));
+            St.row_cost.resize((size_t)2 * order_rows); // [rows] summed claim clocks, [rows] the longest claim
             St.row_capacity = order_rows;
         }
-        CU(cudaMemsetAsync(St.row_cost.ptr, 0, (size_t)order_rows * sizeof(unsigned long long), St.stream));
+        CU(cudaMemsetAsync(St.row_cost.ptr, 0, (size_t)2 * order_rows * sizeof(unsigned long long), St.stream));
         F.row_cost = St.row_cost.ptr;
+        F.row_count = order_rows;
         if (St.claim_reverse) F.flags |= CLPT_F_REVERSE;
     }
     if (p2p) {
@@ -740,7 +746,7 @@ void clpt_state_launch_frame(int width, int height) {
     CU(cudaGetLastError());
     CU(cudaEventRecord(St.ev_stop, St.stream));
     if (order_rows > 0) {
-        CU(cudaMemcpyAsync(St.host_row_cost, St.row_cost.ptr, (size_t)order_rows * sizeof(unsigned long long),
+        CU(cudaMemcpyAsync(St.host_row_cost, St.row_cost.ptr, (size_t)2 * order_rows * sizeof(unsigned long long),
                            cudaMemcpyDeviceToHost, St.stream));
     }
 
@@ -784,6 +790,12 @@ void clpt_state_launch_frame(int width, int height) {
         if (getenv("CLPT_VERBOSE") && atoi(getenv("CLPT_VERBOSE")) >= 3) {
             fprintf(stderr, "CLExecute: costliest rows at %.2f of %d, next frame claims %s\n", where, order_rows,
                     St.claim_reverse ? "bottom-up" : "top-down");
+            if (atoi(getenv("CLPT_VERBOSE")) >= 4) {
+                for (int r = 0; r < order_rows; r++) {
+                    fprintf(stderr, "  row %d: claims %llu kclk in all, longest %llu kclk\n", r,
+                            St.host_row_cost[r] / 1000ull, St.host_row_cost[order_rows + r] / 1000ull);
+                }
+            }
         }
     }
     if (St.flags & CLPT_FLAG_COUNTERS) {
@@ -1057,6 +1069,8 @@ void CLBuildStats(int *nodes, int *tri_refs, int *levels) {
     if (tri_refs) *tri_refs = St.gpu_tree.n_refs;
     if (levels) *levels = St.gpu_tree.levels;
 }
+
+int CLLastBuildWasRecorded(void) { return clpt_gpu_build_was_recorded() ? 1 : 0; }
 
 void CLDownloadKd(kd *out) {
     require_init("CLDownloadKd");

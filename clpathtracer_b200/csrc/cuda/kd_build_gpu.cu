@@ -73,6 +73,17 @@ struct Decision { // what `choose` decided for a node
 struct Triple {
     unsigned l, r, f;
 };
+
+// The counts of the level being split, ON THE DEVICE: every kernel of a level reads them from here,
+// so a whole build can be enqueued (or replayed as a CUDA graph) without the host knowing them.
+struct LevelState {
+    int n_nodes, n_refs;       // this level
+    int n_out, n_leaf_refs;    // wire nodes allocated / leaf references written so far
+    int nx_nodes, nx_refs, nx_leaf; // what `plan` computed for the next level
+    int overflow;              // a capacity was exceeded: the build stopped, the host falls back
+    int levels;                // levels that had nodes
+    int pad[7];
+};
 __host__ __device__ inline Triple operator+(Triple a, Triple b) { return Triple{ a.l + b.l, a.r + b.r, a.f + b.f }; }
 
 // ---- bounds of every triangle (SoA) ---------------------------------------------------
@@ -126,9 +137,14 @@ __global__ void scene_box_kernel(const float *__restrict__ lo, const float *__re
 }
 
 __global__ void root_kernel(const int *__restrict__ box_keys, int n_tris, int max_depth, ANode *__restrict__ nodes,
-                            int *__restrict__ ref_tri, int *__restrict__ ref_node) {
+                            int *__restrict__ ref_tri, int *__restrict__ ref_node, LevelState *__restrict__ ls) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
+        LevelState st = {};
+        st.n_nodes = 1;
+        st.n_refs = n_tris;
+        st.n_out = 1;
+        *ls = st;
         ANode r;
         for (int a = 0; a < 3; a++) {
             r.mn[a] = key_float(box_keys[a]);
@@ -155,12 +171,14 @@ __device__ __forceinline__ int bin_of(float x, float mn, float scale) {
 }
 
 __global__ void __launch_bounds__(256)
-bin_kernel(const ANode *__restrict__ nodes, const int *__restrict__ ref_tri, const int *__restrict__ ref_node,
-           int n_refs, const float *__restrict__ lo, const float *__restrict__ hi, int n_tris, int min_split,
-           unsigned *__restrict__ hist /* [node][axis][start|end][bin] */) {
+bin_kernel(const LevelState *__restrict__ ls, const ANode *__restrict__ nodes, const int *__restrict__ ref_tri,
+           const int *__restrict__ ref_node, const float *__restrict__ lo, const float *__restrict__ hi, int n_tris,
+           int min_split, unsigned *__restrict__ hist /* [node][axis][start|end][bin] */) {
     __shared__ unsigned local[3 * 2 * NBINS];
     __shared__ int home; // histogram slot of the node this block's first reference belongs to (-1: a small node)
+    const int n_refs = ls->n_refs;
     const int first = blockIdx.x * blockDim.x;
+    if (first >= n_refs) return; // (uniform per block)
     if (threadIdx.x == 0) home = nodes[ref_node[min(first, n_refs - 1)]].hist_slot;
     for (int k = threadIdx.x; k < 3 * 2 * NBINS; k += blockDim.x) local[k] = 0;
     __syncthreads();
@@ -217,15 +235,17 @@ constexpr int SMALL_MAX = 8;
 
 template <int W>
 __global__ void __launch_bounds__(256)
-choose_kernel(const ANode *__restrict__ nodes, int n_nodes, const unsigned *__restrict__ hist,
+choose_kernel(const LevelState *__restrict__ ls, const ANode *__restrict__ nodes, const unsigned *__restrict__ hist,
               const int *__restrict__ ref_tri, const float *__restrict__ lo, const float *__restrict__ hi, int n_tris,
               int min_split, float ct, float ci, float empty_bonus, Decision *__restrict__ decisions) {
     const int lane = threadIdx.x & 31, sub = lane & (W - 1);
     const unsigned mask = W == 32 ? 0xffffffffu : (((1u << W) - 1u) << (lane & ~(W - 1)));
-    const int a = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) / W);
-    if (a >= n_nodes) return; // (whole groups leave together: `a` is uniform in a group)
+    const int n_nodes = ls->n_nodes;
+    const int groups = (int)(((size_t)gridDim.x * blockDim.x) / W);
+    // grid-stride over the nodes (whole groups move together: `a` is uniform in a group)
+    for (int a = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) / W); a < n_nodes; a += groups) {
     const ANode nd = nodes[a];
-    if ((W == 8) != (nd.count <= SMALL_MAX)) return; // the other launch's node
+    if ((W == 8) != (nd.count <= SMALL_MAX)) continue; // the other launch's node
     Decision d;
     d.axis = -1;
     d.plane = 0.0f;
@@ -335,6 +355,7 @@ choose_kernel(const ANode *__restrict__ nodes, int n_nodes, const unsigned *__re
         }
     }
     if (sub == 0) decisions[a] = d;
+    }
 }
 
 // ---- scans -----------------------------------------------------------------------------
@@ -356,8 +377,10 @@ __device__ __forceinline__ Triple ref_flags(const ANode *__restrict__ nodes, con
 }
 
 template <typename F>
-__global__ void __launch_bounds__(SCAN_BLOCK) scan_tile_sums_kernel(int n, F f, Triple *__restrict__ tile_sums) {
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_tile_sums_kernel(const int *__restrict__ n_ptr, F f,
+                                                                     Triple *__restrict__ tile_sums) {
     __shared__ Triple warp_sums[SCAN_BLOCK / 32];
+    const int n = *n_ptr;
     const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     Triple s = { 0u, 0u, 0u };
 #pragma unroll
@@ -408,10 +431,12 @@ __global__ void __launch_bounds__(1024) scan_tile_offsets_kernel(Triple *__restr
 
 // Exclusive scan values for every item (plus one past the end = totals).
 template <typename F>
-__global__ void __launch_bounds__(SCAN_BLOCK) scan_write_kernel(int n, F f, const Triple *__restrict__ tile_offsets,
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_write_kernel(const int *__restrict__ n_ptr, F f,
+                                                                const Triple *__restrict__ tile_offsets,
                                                                 const Triple *__restrict__ total,
                                                                 Triple *__restrict__ out /* n + 1 */) {
     __shared__ Triple warp_sums[SCAN_BLOCK / 32];
+    const int n = *n_ptr;
     const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     Triple v[SCAN_ITEMS];
     Triple s = { 0u, 0u, 0u };
@@ -467,12 +492,13 @@ __device__ __forceinline__ void write_box(int *__restrict__ wire, int out, const
     w[7] = 0;
 }
 
-__global__ void emit_kernel(const ANode *__restrict__ nodes, int n_nodes, const Decision *__restrict__ dec,
-                            const Triple *__restrict__ node_scan /* n_nodes + 1 */,
-                            const Triple *__restrict__ ref_scan /* n_refs + 1 */, int next_out_base, int leaf_ref_base,
-                            int *__restrict__ wire, ANode *__restrict__ next_nodes, int *__restrict__ big_counter) {
+__global__ void emit_kernel(const LevelState *__restrict__ ls, const ANode *__restrict__ nodes,
+                            const Decision *__restrict__ dec, const Triple *__restrict__ node_scan /* n_nodes + 1 */,
+                            const Triple *__restrict__ ref_scan /* n_refs + 1 */, int *__restrict__ wire,
+                            ANode *__restrict__ next_nodes, int *__restrict__ big_counter) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= n_nodes) return;
+    if (a >= ls->n_nodes) return;
+    const int next_out_base = ls->n_out, leaf_ref_base = ls->n_leaf_refs;
     const ANode nd = nodes[a];
     const Decision d = dec[a];
     write_box(wire, nd.out, nd.mn, nd.mx);
@@ -515,11 +541,13 @@ __global__ void emit_kernel(const ANode *__restrict__ nodes, int n_nodes, const 
 
 __global__ void scatter_kernel(const ANode *__restrict__ nodes, const Decision *__restrict__ dec,
                                const Triple *__restrict__ node_scan, const Triple *__restrict__ ref_scan,
-                               const int *__restrict__ ref_tri, const int *__restrict__ ref_node, int n_refs,
-                               const float *__restrict__ lo, const float *__restrict__ hi, int n_tris, int leaf_ref_base,
-                               int *__restrict__ next_tri, int *__restrict__ next_node, int *__restrict__ tri_indices) {
+                               const int *__restrict__ ref_tri, const int *__restrict__ ref_node,
+                               const LevelState *__restrict__ ls, const float *__restrict__ lo,
+                               const float *__restrict__ hi, int n_tris, int *__restrict__ next_tri,
+                               int *__restrict__ next_node, int *__restrict__ tri_indices) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_refs) return;
+    if (i >= ls->n_refs) return;
+    const int leaf_ref_base = ls->n_leaf_refs;
     const int a = ref_node[i], t = ref_tri[i];
     const Triple here = ref_scan[i];
     const Triple fl = ref_flags(nodes, dec, ref_tri, ref_node, lo, hi, n_tris, i);
@@ -543,13 +571,43 @@ __global__ void scatter_kernel(const ANode *__restrict__ nodes, const Decision *
     }
 }
 
+// ---- level bookkeeping on the device ------------------------------------------------------
+// After the scans: what the next level will hold, checked against the capacities of the buffers
+// the level's emit and scatter are about to write.  Over capacity -> the build stops here (this
+// level and all later ones become empty) and `overflow` tells the host, which falls back to the
+// path that sizes every level exactly.
+__global__ void plan_kernel(LevelState *__restrict__ ls, const Triple *__restrict__ ref_total,
+                            const Triple *__restrict__ node_total, int cap_nodes_next, int cap_refs, int cap_out,
+                            int cap_leaf) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    long long nx_nodes = 2ll * node_total->l, nx_refs = (long long)ref_total->l + ref_total->r, nx_leaf = ref_total->f;
+    if (ls->n_nodes > 0) ls->levels++;
+    if (ls->n_out + nx_nodes > cap_out || ls->n_leaf_refs + nx_leaf > cap_leaf || nx_refs > cap_refs ||
+        nx_nodes > cap_nodes_next) {
+        ls->overflow = 1;
+        ls->n_nodes = ls->n_refs = 0;
+        nx_nodes = nx_refs = nx_leaf = 0;
+    }
+    ls->nx_nodes = (int)nx_nodes;
+    ls->nx_refs = (int)nx_refs;
+    ls->nx_leaf = (int)nx_leaf;
+}
+
+__global__ void commit_kernel(LevelState *__restrict__ ls) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    ls->n_out += ls->nx_nodes;
+    ls->n_leaf_refs += ls->nx_leaf;
+    ls->n_nodes = ls->nx_nodes;
+    ls->n_refs = ls->nx_refs;
+}
+
 // ---- ropes -----------------------------------------------------------------------------
 // One thread per (node, face): a leaf's link is pushed down to the deepest node that the
 // whole face still looks into (kd_build.c: push_down_link with full = 1).
-__global__ void push_ropes_kernel(int *__restrict__ wire, int n_nodes) {
+__global__ void push_ropes_kernel(int *__restrict__ wire, const LevelState *__restrict__ ls) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int node = i / 6, face = i - node * 6;
-    if (node >= n_nodes) return;
+    if (node >= ls->n_out) return;
     int *w = wire + 17 * (size_t)node;
     if (w[8] != 1) return;
     int link = w[11 + face];
@@ -573,9 +631,13 @@ __global__ void push_ropes_kernel(int *__restrict__ wire, int n_nodes) {
     w[11 + face] = link;
 }
 
+bool g_last_build_recorded = false;
+size_t g_reallocations = 0; // (a recorded build holds raw pointers: it is re-recorded when any buffer moved)
+
 template <typename T>
 void ensure(T *&ptr, size_t &cap, size_t want) {
     if (want <= cap) return;
+    g_reallocations++;
     if (ptr) CU(cudaFree(ptr));
     const size_t n = want + want / 4 + 1024;
     CU(cudaMalloc((void **)&ptr, n * sizeof(T)));
@@ -596,18 +658,182 @@ struct Workspace {
     size_t hist_cap = 0;
     Triple *ref_scan = nullptr, *node_scan = nullptr, *tiles = nullptr, *totals = nullptr;
     size_t ref_scan_cap = 0, node_scan_cap = 0, tiles_cap = 0, totals_cap = 0;
-    int *box_keys = nullptr, *bad = nullptr;
-    size_t box_cap = 0, bad_cap = 0;
-    Triple *host_totals = nullptr; // pinned: [0] references, [1] nodes
+    int *box_keys = nullptr, *bad = nullptr, *box_init = nullptr;
+    size_t box_cap = 0, bad_cap = 0, box_init_cap = 0;
+    LevelState *level = nullptr; // [0] the build's, [1] scratch (`n` of a stand-alone scan)
+    size_t level_cap = 0;
+    struct Pinned { // what comes back to the host
+        Triple totals[2]; // [0] references, [1] nodes
+        int bad;
+        int n;
+        LevelState level;
+    } *host = nullptr;
+    // the whole build of a small mesh, recorded once and replayed (see clpt_gpu_build)
+    cudaGraphExec_t graph = nullptr;
+    struct GraphKey {
+        const void *verts, *corners, *wire, *tri_indices;
+        size_t reallocations, room;
+        int n_verts, n_tris, max_depth, min_split;
+        float ct, ci, empty_bonus;
+        bool operator==(const GraphKey &o) const {
+            return verts == o.verts && corners == o.corners && wire == o.wire && tri_indices == o.tri_indices &&
+                   reallocations == o.reallocations && room == o.room && n_verts == o.n_verts && n_tris == o.n_tris && max_depth == o.max_depth && min_split == o.min_split &&
+                   ct == o.ct && ci == o.ci && empty_bonus == o.empty_bonus;
+        }
+    } graph_key = {};
+    int graph_refused_tris = -1, graph_refused_room = 0; // the recorded capacities were too small for a mesh of this size: do not try again
 } W;
 
+void ensure_host() {
+    if (!W.host) CU(cudaMallocHost((void **)&W.host, sizeof(Workspace::Pinned)));
+    ensure(W.level, W.level_cap, (size_t)2);
+    ensure(W.totals, W.totals_cap, (size_t)2);
+}
+
+void drop_graph() {
+    if (W.graph) (void)cudaGraphExecDestroy(W.graph);
+    W.graph = nullptr;
+}
+
+// Scan of f(0..n-1), n read from device memory; `n_cap` (>= n) sizes the launch.
 template <typename F>
-void scan(int n, F f, Triple *out, Triple *total_dev, cudaStream_t s) {
-    const int tiles = std::max(1, (n + SCAN_TILE - 1) / SCAN_TILE);
-    ensure(W.tiles, W.tiles_cap, (size_t)tiles);
-    scan_tile_sums_kernel<<<tiles, SCAN_BLOCK, 0, s>>>(n, f, W.tiles);
+void scan(const int *n_ptr, int n_cap, F f, Triple *out, Triple *total_dev, cudaStream_t s) {
+    const int tiles = std::max(1, (n_cap + SCAN_TILE - 1) / SCAN_TILE);
+    scan_tile_sums_kernel<<<tiles, SCAN_BLOCK, 0, s>>>(n_ptr, f, W.tiles);
     scan_tile_offsets_kernel<<<1, 1024, 0, s>>>(W.tiles, tiles, total_dev);
-    scan_write_kernel<<<tiles, SCAN_BLOCK, 0, s>>>(n, f, W.tiles, total_dev, out);
+    scan_write_kernel<<<tiles, SCAN_BLOCK, 0, s>>>(n_ptr, f, W.tiles, total_dev, out);
+}
+
+int scan_tiles(size_t n_cap) { return (int)std::max<size_t>(1, (n_cap + SCAN_TILE - 1) / SCAN_TILE); }
+
+constexpr int T = 256;
+constexpr int CHOOSE_MAX_BLOCKS = 148 * 16;
+
+struct BuildArgs {
+    const float4 *verts;
+    const int4 *corners;
+    int n_verts, n_tris, max_depth, min_split;
+    float ct, ci, empty_bonus;
+};
+
+// Triangle bounds, scene box, the root node and its reference list, the level state.
+void enqueue_prologue(const BuildArgs &A, cudaStream_t s) {
+    CU(cudaMemsetAsync(W.bad, 0, sizeof(int), s));
+    tri_bounds_kernel<<<(A.n_tris + T - 1) / T, T, 0, s>>>(A.verts, A.corners, A.n_tris, A.n_verts, W.lo, W.hi, W.bad);
+    CU(cudaMemcpyAsync(W.box_keys, W.box_init, 6 * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    scene_box_kernel<<<std::min(1024, (A.n_tris + T - 1) / T), T, 0, s>>>(W.lo, W.hi, A.n_tris, W.box_keys);
+    CU(cudaMemcpyAsync(&W.host->bad, W.bad, sizeof(int), cudaMemcpyDeviceToHost, s));
+    root_kernel<<<(A.n_tris + T - 1) / T, T, 0, s>>>(W.box_keys, A.n_tris, A.max_depth, W.nodes[0], W.ref_tri[0],
+                                                     W.ref_node[0], W.level);
+}
+
+// The first half of a level: histograms, the split decisions, the two scans.  `refs` and
+// `nodes` size the launches (the true counts, or upper bounds -- the kernels read the true
+// counts from the level state).
+void enqueue_decide(const BuildArgs &A, int cur, size_t refs, size_t nodes, cudaStream_t s) {
+    const LevelState *ls = W.level;
+    const size_t hist_slots = refs / (EXACT_MAX + 1) + 1; // nodes with histograms hold more than EXACT_MAX references
+    CU(cudaMemsetAsync(W.hist, 0, hist_slots * 3 * 2 * NBINS * sizeof(unsigned), s));
+    if (refs > 0) {
+        bin_kernel<<<(unsigned)((refs + 255) / 256), 256, 0, s>>>(ls, W.nodes[cur], W.ref_tri[cur], W.ref_node[cur], W.lo,
+                                                                  W.hi, A.n_tris, A.min_split, W.hist);
+    }
+    const unsigned g32 = (unsigned)std::min<size_t>(CHOOSE_MAX_BLOCKS, (nodes * 32 + 255) / 256);
+    const unsigned g8 = (unsigned)std::min<size_t>(CHOOSE_MAX_BLOCKS, (nodes * 8 + 255) / 256);
+    choose_kernel<32><<<std::max(1u, g32), 256, 0, s>>>(ls, W.nodes[cur], W.hist, W.ref_tri[cur], W.lo, W.hi, A.n_tris,
+                                                        A.min_split, A.ct, A.ci, A.empty_bonus, W.dec);
+    choose_kernel<8><<<std::max(1u, g8), 256, 0, s>>>(ls, W.nodes[cur], W.hist, W.ref_tri[cur], W.lo, W.hi, A.n_tris,
+                                                      A.min_split, A.ct, A.ci, A.empty_bonus, W.dec);
+    RefFlagFn rf{ W.nodes[cur], W.dec, W.ref_tri[cur], W.ref_node[cur], W.lo, W.hi, A.n_tris };
+    scan(&ls->n_refs, (int)refs, rf, W.ref_scan, W.totals, s);
+    SplitFlagFn sf{ W.dec };
+    scan(&ls->n_nodes, (int)nodes, sf, W.node_scan, W.totals + 1, s);
+}
+
+// The second half: capacities checked on the device, wire nodes and the next level's nodes
+// written, references moved to their children or to the leaf lists, the level state advanced.
+void enqueue_split(const BuildArgs &A, int cur, size_t refs, size_t nodes, int cap_nodes_next, int cap_refs, int cap_out,
+                   int cap_leaf, ClptGpuTree &out, cudaStream_t s) {
+    const int nxt = cur ^ 1;
+    plan_kernel<<<1, 32, 0, s>>>(W.level, W.totals, W.totals + 1, cap_nodes_next, cap_refs, cap_out, cap_leaf);
+    CU(cudaMemsetAsync(W.bad, 0, sizeof(int), s)); // doubles as the histogram-slot counter of the next level
+    emit_kernel<<<(unsigned)std::max<size_t>(1, (nodes + T - 1) / T), T, 0, s>>>(W.level, W.nodes[cur], W.dec, W.node_scan,
+                                                                                 W.ref_scan, out.wire, W.nodes[nxt], W.bad);
+    if (refs > 0) {
+        scatter_kernel<<<(unsigned)((refs + T - 1) / T), T, 0, s>>>(W.nodes[cur], W.dec, W.node_scan, W.ref_scan,
+                                                                    W.ref_tri[cur], W.ref_node[cur], W.level, W.lo, W.hi,
+                                                                    A.n_tris, W.ref_tri[nxt], W.ref_node[nxt],
+                                                                    out.tri_indices);
+    }
+    commit_kernel<<<1, 32, 0, s>>>(W.level);
+}
+
+// Meshes up to this size are built without the host in the loop (below).
+constexpr int GRAPH_MAX_TRIS = 1 << 18;
+
+// One recording of the WHOLE build for small meshes: every level's launches sized by fixed
+// capacities, the counts living in the level state, max_depth + 1 levels whatever the tree
+// turns out to need (levels past the last are empty launches).  The recording is replayed
+// while mesh size, buffers and parameters stay the same -- an animated scene.  Returns
+// false if the capacities were too small (the caller then takes the level-by-level path).
+bool build_recorded(const BuildArgs &A, int room_pc, ClptGpuTree &out, cudaStream_t s, char *err, size_t errlen,
+                    bool *bad_mesh) {
+    const size_t n = (size_t)A.n_tris;
+    size_t cap_refs = 6 * n + 4096, cap_nodes = 4 * n + 1024, cap_out = 8 * n + 4096, cap_leaf = 8 * n + 4096;
+    if (room_pc != 100) {
+        const size_t pc = (size_t)room_pc;
+        cap_refs = std::max(n, cap_refs * pc / 100), cap_nodes = std::max<size_t>(2, cap_nodes * pc / 100);
+        cap_out = std::max<size_t>(2, cap_out * pc / 100), cap_leaf = std::max<size_t>(2, cap_leaf * pc / 100);
+    }
+    for (int k = 0; k < 2; k++) {
+        ensure(W.ref_tri[k], W.ref_cap[k][0], cap_refs);
+        ensure(W.ref_node[k], W.ref_cap[k][1], cap_refs);
+        ensure(W.nodes[k], W.node_cap[k], cap_nodes);
+    }
+    ensure(W.dec, W.dec_cap, cap_nodes);
+    ensure(W.hist, W.hist_cap, (cap_refs / (EXACT_MAX + 1) + 1) * 3 * 2 * NBINS);
+    ensure(W.ref_scan, W.ref_scan_cap, cap_refs + 1);
+    ensure(W.node_scan, W.node_scan_cap, cap_nodes + 1);
+    ensure(W.tiles, W.tiles_cap, (size_t)scan_tiles(cap_out)); // (also what the re-layout of this tree will ask for)
+    ensure(out.wire, out.wire_cap, cap_out * 17);
+    ensure(out.tri_indices, out.tri_indices_cap, cap_leaf);
+    const Workspace::GraphKey key = { A.verts, A.corners, out.wire, out.tri_indices, g_reallocations, cap_refs, A.n_verts, A.n_tris,
+                                      A.max_depth, A.min_split, A.ct, A.ci, A.empty_bonus };
+    if (!W.graph || !(key == W.graph_key)) {
+        drop_graph();
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        enqueue_prologue(A, s);
+        int cur = 0;
+        for (int level = 0; level <= A.max_depth; level++) {
+            // a level has at most 2^level nodes, and its references all come from the level above
+            const size_t nodes = level < 30 ? std::min<size_t>(cap_nodes, (size_t)1 << level) : cap_nodes;
+            const size_t nodes_next = level + 1 < 30 ? std::min<size_t>(cap_nodes, (size_t)2 << level) : cap_nodes;
+            const size_t refs = level == 0 ? n : cap_refs;
+            enqueue_decide(A, cur, refs, nodes, s);
+            enqueue_split(A, cur, refs, nodes, (int)nodes_next, (int)cap_refs, (int)cap_out, (int)cap_leaf, out, s);
+            cur ^= 1;
+        }
+        push_ropes_kernel<<<(unsigned)((cap_out * 6 + T - 1) / T), T, 0, s>>>(out.wire, W.level);
+        CU(cudaMemcpyAsync(&W.host->level, W.level, sizeof(LevelState), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamEndCapture(s, &g));
+        CU(cudaGraphInstantiate(&W.graph, g, 0));
+        CU(cudaGraphDestroy(g));
+        W.graph_key = key;
+    }
+    CU(cudaGraphLaunch(W.graph, s));
+    CU(cudaStreamSynchronize(s));
+    if (W.host->bad) {
+        *bad_mesh = true;
+        snprintf(err, errlen, "triangle corner references a missing vertex");
+        return false;
+    }
+    const LevelState &L = W.host->level;
+    if (L.overflow || L.n_nodes != 0) return false; // (n_nodes != 0: deeper than max_depth cannot happen; belt and braces)
+    out.n_nodes = L.n_out;
+    out.n_refs = L.n_leaf_refs;
+    out.levels = L.levels;
+    return true;
 }
 
 } // namespace
@@ -618,71 +844,69 @@ bool clpt_gpu_build(const float4 *verts, int n_verts, const int4 *corners, int n
         snprintf(err, errlen, "empty mesh");
         return false;
     }
-    const int T = 256;
+    BuildArgs A = { verts, corners, n_verts, n_tris, P.max_depth, P.min_split > 1 ? P.min_split : 2, P.ct, P.ci,
+                    P.empty_bonus };
+    if (A.max_depth <= 0) { // 8 + 1.3 log2(N), the usual bound for SAH kd-trees
+        int lg = 0;
+        while ((1 << lg) < n_tris) lg++;
+        A.max_depth = 8 + (13 * lg) / 10;
+    }
+    ensure_host();
     ensure(W.lo, W.bounds_cap, (size_t)n_tris * 3);
     ensure(W.hi, W.bounds_cap2, (size_t)n_tris * 3);
     ensure(W.box_keys, W.box_cap, (size_t)8);
     ensure(W.bad, W.bad_cap, (size_t)1);
-    ensure(W.totals, W.totals_cap, (size_t)2);
-    if (!W.host_totals) CU(cudaMallocHost((void **)&W.host_totals, 2 * sizeof(Triple) + 64));
-    int *host_bad = reinterpret_cast<int *>(W.host_totals + 2);
-    CU(cudaMemsetAsync(W.bad, 0, sizeof(int), s));
-    tri_bounds_kernel<<<(n_tris + T - 1) / T, T, 0, s>>>(verts, corners, n_tris, n_verts, W.lo, W.hi, W.bad);
-    const int init_keys[6] = { INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN };
-    CU(cudaMemcpyAsync(W.box_keys, init_keys, sizeof(init_keys), cudaMemcpyHostToDevice, s));
-    scene_box_kernel<<<std::min(1024, (n_tris + T - 1) / T), T, 0, s>>>(W.lo, W.hi, n_tris, W.box_keys);
-    CU(cudaMemcpyAsync(host_bad, W.bad, sizeof(int), cudaMemcpyDeviceToHost, s));
-
-    int max_depth = P.max_depth;
-    if (max_depth <= 0) { // 8 + 1.3 log2(N), the usual bound for SAH kd-trees
-        int lg = 0;
-        while ((1 << lg) < n_tris) lg++;
-        max_depth = 8 + (13 * lg) / 10;
+    if (!W.box_init) {
+        ensure(W.box_init, W.box_init_cap, (size_t)8);
+        const int init_keys[6] = { INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN };
+        CU(cudaMemcpy(W.box_init, init_keys, sizeof(init_keys), cudaMemcpyHostToDevice));
     }
-    const int min_split = P.min_split > 1 ? P.min_split : 2;
 
+    const char *no_graph = getenv("CLPT_BUILD_NO_GRAPH"); // measurement and tests: always level by level
+    const char *room = getenv("CLPT_BUILD_RECORD_ROOM"); // tests: per cent of the usual room, to meet the fallback
+    const int room_pc = room ? std::max(1, atoi(room)) : 100;
+    const bool refused = W.graph_refused_tris == n_tris && W.graph_refused_room == room_pc;
+    if (n_tris <= GRAPH_MAX_TRIS && !refused && !(no_graph && atoi(no_graph) != 0)) {
+        bool bad_mesh = false;
+        if (build_recorded(A, room_pc, out, s, err, errlen, &bad_mesh)) {
+            g_last_build_recorded = true;
+            return true;
+        }
+        if (bad_mesh) return false;
+        W.graph_refused_room = room_pc;
+        W.graph_refused_tris = n_tris; // this mesh needs more room than the recording gives: size every level exactly
+        drop_graph();
+    }
+    g_last_build_recorded = false;
+
+    // Level by level with the host in the loop: two counters come back per level to size the
+    // next level's buffers and launches exactly (any mesh size).
     int cur = 0;
     ensure(W.ref_tri[0], W.ref_cap[0][0], (size_t)n_tris);
     ensure(W.ref_node[0], W.ref_cap[0][1], (size_t)n_tris);
     ensure(W.nodes[0], W.node_cap[0], (size_t)1);
-    root_kernel<<<(n_tris + T - 1) / T, T, 0, s>>>(W.box_keys, n_tris, max_depth, W.nodes[0], W.ref_tri[0], W.ref_node[0]);
-
-    // output arrays grow as the levels come in
-    size_t n_out = 1;        // wire nodes allocated so far (the root)
-    size_t n_leaf_refs = 0;  // tri_indices written so far
-    int n_nodes = 1, n_refs = n_tris;
+    enqueue_prologue(A, s);
+    size_t n_out = 1;       // wire nodes allocated so far (the root)
+    size_t n_leaf_refs = 0; // tri_indices written so far
+    size_t n_nodes = 1, n_refs = (size_t)n_tris;
     ensure(out.wire, out.wire_cap, (size_t)17 * 1024);
     int levels = 0;
     while (n_nodes > 0) {
         levels++;
-        ensure(W.dec, W.dec_cap, (size_t)n_nodes);
-        // nodes with histograms hold more than EXACT_MAX references each
-        const size_t hist_slots = (size_t)n_refs / (EXACT_MAX + 1) + 1;
-        ensure(W.hist, W.hist_cap, hist_slots * 3 * 2 * NBINS);
-        ensure(W.ref_scan, W.ref_scan_cap, (size_t)n_refs + 1);
-        ensure(W.node_scan, W.node_scan_cap, (size_t)n_nodes + 1);
-        CU(cudaMemsetAsync(W.hist, 0, hist_slots * 3 * 2 * NBINS * sizeof(unsigned), s));
-        if (n_refs > 0) {
-            bin_kernel<<<(n_refs + 255) / 256, 256, 0, s>>>(W.nodes[cur], W.ref_tri[cur], W.ref_node[cur], n_refs, W.lo,
-                                                            W.hi, n_tris, min_split, W.hist);
-        }
-        choose_kernel<32><<<(unsigned)(((size_t)n_nodes * 32 + 255) / 256), 256, 0, s>>>(
-            W.nodes[cur], n_nodes, W.hist, W.ref_tri[cur], W.lo, W.hi, n_tris, min_split, P.ct, P.ci, P.empty_bonus, W.dec);
-        choose_kernel<8><<<(unsigned)(((size_t)n_nodes * 8 + 255) / 256), 256, 0, s>>>(
-            W.nodes[cur], n_nodes, W.hist, W.ref_tri[cur], W.lo, W.hi, n_tris, min_split, P.ct, P.ci, P.empty_bonus, W.dec);
-        RefFlagFn rf{ W.nodes[cur], W.dec, W.ref_tri[cur], W.ref_node[cur], W.lo, W.hi, n_tris };
-        scan(n_refs, rf, W.ref_scan, W.totals, s);
-        SplitFlagFn sf{ W.dec };
-        scan(n_nodes, sf, W.node_scan, W.totals + 1, s);
-        CU(cudaMemcpyAsync(W.host_totals, W.totals, 2 * sizeof(Triple), cudaMemcpyDeviceToHost, s));
+        ensure(W.dec, W.dec_cap, n_nodes);
+        ensure(W.hist, W.hist_cap, (n_refs / (EXACT_MAX + 1) + 1) * 3 * 2 * NBINS);
+        ensure(W.ref_scan, W.ref_scan_cap, n_refs + 1);
+        ensure(W.node_scan, W.node_scan_cap, n_nodes + 1);
+        ensure(W.tiles, W.tiles_cap, (size_t)scan_tiles(std::max(n_refs, n_nodes)));
+        enqueue_decide(A, cur, n_refs, n_nodes, s);
+        CU(cudaMemcpyAsync(W.host->totals, W.totals, 2 * sizeof(Triple), cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
-        if (levels == 1 && *host_bad) {
+        if (levels == 1 && W.host->bad) {
             snprintf(err, errlen, "triangle corner references a missing vertex");
             return false;
         }
-        const Triple rt = W.host_totals[0], nt = W.host_totals[1];
-        const int n_splits = (int)nt.l;
-        const size_t next_refs = (size_t)rt.l + rt.r, next_nodes = (size_t)2 * n_splits;
+        const Triple rt = W.host->totals[0], nt = W.host->totals[1];
+        const size_t next_refs = (size_t)rt.l + rt.r, next_nodes = (size_t)2 * nt.l;
         if (next_refs > 0x7fff0000u || n_out + next_nodes > 0x1fff0000u) {
             snprintf(err, errlen, "tree too large (%zu references, %zu nodes)", next_refs, n_out + next_nodes);
             return false;
@@ -714,22 +938,14 @@ bool clpt_gpu_build(const float4 *verts, int n_verts, const int4 *corners, int n
         ensure(W.ref_tri[nxt], W.ref_cap[nxt][0], next_refs);
         ensure(W.ref_node[nxt], W.ref_cap[nxt][1], next_refs);
         ensure(W.nodes[nxt], W.node_cap[nxt], next_nodes);
-        CU(cudaMemsetAsync(W.bad, 0, sizeof(int), s)); // doubles as the histogram-slot counter of the next level
-        emit_kernel<<<(n_nodes + T - 1) / T, T, 0, s>>>(W.nodes[cur], n_nodes, W.dec, W.node_scan, W.ref_scan, (int)n_out,
-                                                        (int)n_leaf_refs, out.wire, W.nodes[nxt], W.bad);
-        if (n_refs > 0) {
-            scatter_kernel<<<(n_refs + T - 1) / T, T, 0, s>>>(W.nodes[cur], W.dec, W.node_scan, W.ref_scan, W.ref_tri[cur],
-                                                              W.ref_node[cur], n_refs, W.lo, W.hi, n_tris,
-                                                              (int)n_leaf_refs, W.ref_tri[nxt], W.ref_node[nxt],
-                                                              out.tri_indices);
-        }
+        enqueue_split(A, cur, n_refs, n_nodes, INT_MAX, INT_MAX, INT_MAX, INT_MAX, out, s);
         n_out += next_nodes;
         n_leaf_refs += rt.f;
-        n_nodes = (int)next_nodes;
-        n_refs = (int)next_refs;
+        n_nodes = next_nodes;
+        n_refs = next_refs;
         cur = nxt;
     }
-    push_ropes_kernel<<<(unsigned)((n_out * 6 + T - 1) / T), T, 0, s>>>(out.wire, (int)n_out);
+    push_ropes_kernel<<<(unsigned)((n_out * 6 + T - 1) / T), T, 0, s>>>(out.wire, W.level);
     CU(cudaGetLastError());
     out.n_nodes = (int)n_out;
     out.n_refs = (int)n_leaf_refs;
@@ -868,23 +1084,26 @@ size_t g_wire_scan_cap = 0;
 bool clpt_gpu_pack(const ClptGpuTree &tree, const float4 *verts, const int4 *corners, int n_prims, ClptGpuPacked &out,
                    cudaStream_t s, char *err, size_t errlen) {
     (void)n_prims;
-    const int n = tree.n_nodes, T = 256;
+    const int n = tree.n_nodes;
     if (n <= 0) {
         snprintf(err, errlen, "empty node array");
         return false;
     }
+    ensure_host();
     ensure(g_new_of, g_new_of_cap, (size_t)n);
     ensure(g_wire_scan, g_wire_scan_cap, (size_t)n + 1);
-    ensure(W.totals, W.totals_cap, (size_t)2);
-    if (!W.host_totals) CU(cudaMallocHost((void **)&W.host_totals, 2 * sizeof(Triple) + 64));
+    ensure(W.tiles, W.tiles_cap, (size_t)scan_tiles((size_t)n));
+    W.host->n = n;
+    int *n_dev = &W.level[1].n_nodes;
+    CU(cudaMemcpyAsync(n_dev, &W.host->n, sizeof(int), cudaMemcpyHostToDevice, s));
     WireTypeFn tf{ tree.wire };
-    scan(n, tf, g_wire_scan, W.totals, s);
-    CU(cudaMemcpyAsync(W.host_totals, W.totals, sizeof(Triple), cudaMemcpyDeviceToHost, s));
+    scan(n_dev, n, tf, g_wire_scan, W.totals, s);
+    CU(cudaMemcpyAsync(W.host->totals, W.totals, sizeof(Triple), cudaMemcpyDeviceToHost, s));
     float box[8];
     CU(cudaMemcpyAsync(box, tree.wire, sizeof(box), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    const int n_splits = (int)W.host_totals[0].l, n_leaves = (int)W.host_totals[0].f;
-    out.fat_refs = W.host_totals[0].r;
+    const int n_splits = (int)W.host->totals[0].l, n_leaves = (int)W.host->totals[0].f;
+    out.fat_refs = W.host->totals[0].r;
     out.n_nodes = 1 + 2 * n_splits;
     out.n_leaves = n_leaves;
     out.n_refs = tree.n_refs;
@@ -925,6 +1144,8 @@ bool clpt_gpu_pack(const ClptGpuTree &tree, const float4 *verts, const int4 *cor
     return true;
 }
 
+bool clpt_gpu_build_was_recorded(void) { return g_last_build_recorded; }
+
 void clpt_gpu_build_release(void) {
     auto drop = [](auto *&p) {
         if (p) (void)cudaFree(p);
@@ -932,10 +1153,12 @@ void clpt_gpu_build_release(void) {
     };
     drop(W.lo), drop(W.hi), drop(W.ref_tri[0]), drop(W.ref_tri[1]), drop(W.ref_node[0]), drop(W.ref_node[1]);
     drop(W.nodes[0]), drop(W.nodes[1]), drop(W.dec), drop(W.hist), drop(W.ref_scan), drop(W.node_scan);
-    drop(W.tiles), drop(W.totals), drop(W.box_keys), drop(W.bad);
+    drop(W.tiles), drop(W.totals), drop(W.box_keys), drop(W.bad), drop(W.box_init), drop(W.level);
     drop(g_new_of), drop(g_wire_scan);
     g_new_of_cap = g_wire_scan_cap = 0;
-    if (W.host_totals) (void)cudaFreeHost(W.host_totals);
+    if (W.host) (void)cudaFreeHost(W.host);
+    drop_graph();
     W = Workspace();
+    g_last_build_recorded = false;
 }
 

@@ -21,10 +21,15 @@ struct ClptGpuTree {
 };
 
 // Builds the tree of `n_tris` triangles (corners: three int4 {v, vn, vt, 0} per triangle,
-// verts: float4) on stream `s`.  Synchronises the stream once per level (two counters come
-// back to size the next level's launches).  False + message on malformed input.
+// verts: float4) on stream `s`.  Meshes of up to 2^18 triangles: the whole build is one recorded
+// CUDA graph (level counts stay on the device, launches sized by fixed capacities), replayed
+// while mesh size and buffers stay the same, one synchronisation at the end.  Larger meshes,
+// or a mesh that outgrows the recorded capacities: level by level, one synchronisation per
+// level (two counters come back to size the next level exactly).  Both give the same tree.
+// False + message on malformed input.
 bool clpt_gpu_build(const float4 *verts, int n_verts, const int4 *corners, int n_tris, const ClptGpuBuildParams &P,
                     ClptGpuTree &out, cudaStream_t s, char *err, size_t errlen);
+bool clpt_gpu_build_was_recorded(void); // the last build ran as the recorded graph
 void clpt_gpu_build_release(void);
 
 // Device twin of clpt_pack_scene (scene_pack.cpp): wire format -> traversal layout

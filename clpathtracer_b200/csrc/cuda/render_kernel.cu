@@ -269,7 +269,9 @@ render_kernel(const __grid_constant__ ClptScene S, const __grid_constant__ ClptF
                 else store_pixel(F, x, ly, acc, spp);
             }
             if (lane == 0 && F.row_cost) {
-                atomicAdd(F.row_cost + tile_row[warp], (unsigned long long)((unsigned)clock() - tile_t0[warp]));
+                const unsigned long long took = (unsigned long long)((unsigned)clock() - tile_t0[warp]);
+                atomicAdd(F.row_cost + tile_row[warp], took);
+                atomicMax(F.row_cost + F.row_count + tile_row[warp], took);
             }
         }
     }

@@ -135,6 +135,13 @@ void CLUpdateVertices(size_t first_vertex, const void *verts, size_t vert_bytes)
 void CLRebuildMeshes(void);
 void CLLastBuildMs(float *build_ms, float *pack_ms); /* device time of the last CLBuildMeshes */
 void CLBuildStats(int *nodes, int *tri_refs, int *levels);
+/* Meshes of up to 2^18 triangles are built without the host in the loop: the launches of
+ * every level are recorded once (a CUDA graph, level counts in device memory, launch sizes
+ * from fixed capacities) and replayed by every later CLRebuildMeshes of the same mesh size.
+ * Larger meshes, and any mesh that outgrows the recorded capacities, are built level by
+ * level with one synchronisation per level; the tree is the same either way.  1 if the
+ * last build was the recorded one.  $CLPT_BUILD_NO_GRAPH=1 forces level by level. */
+int CLLastBuildWasRecorded(void);
 /* The tree CLBuildMeshes built, as a regular `kd` (fresh host lists the caller owns and
  * frees with delete_kd): what the oracle walks in the parity tests, and what write_kd
  * can cache. */

@@ -139,6 +139,35 @@ def test_device_build_is_deterministic(clpt, renderer):
     assert a.nodes.tobytes() == b.nodes.tobytes() and a.tri_indices.tobytes() == b.tri_indices.tobytes()
 
 
+@pytest.mark.parametrize("name", ["hf60", "soup3000", "hf224"])
+def test_recorded_build_equals_level_by_level(clpt, renderer, monkeypatch, name):
+    """Small meshes are built by replaying one recorded graph (level counts on the device, launches
+    sized by capacities); the level-by-level path sizes every level exactly from counters read back.
+    Same tree byte for byte -- also when the mesh outgrows the recorded capacities half way and the
+    build starts over level by level, and on a replay."""
+    v, c, n = _mesh(name)
+    monkeypatch.delenv("CLPT_BUILD_NO_GRAPH", raising=False)
+    monkeypatch.delenv("CLPT_BUILD_RECORD_ROOM", raising=False)
+    renderer.build_meshes(v, c, n)
+    assert renderer.build_was_recorded()
+    a = renderer.download_kd()
+    renderer.rebuild_meshes()  # the replay
+    assert renderer.build_was_recorded()
+    a2 = renderer.download_kd()
+    monkeypatch.setenv("CLPT_BUILD_NO_GRAPH", "1")
+    renderer.build_meshes(v, c, n)
+    assert not renderer.build_was_recorded()
+    b = renderer.download_kd()
+    monkeypatch.delenv("CLPT_BUILD_NO_GRAPH")
+    monkeypatch.setenv("CLPT_BUILD_RECORD_ROOM", "12")  # an eighth of the room: overflows some levels down
+    renderer.build_meshes(v, c, n)
+    assert not renderer.build_was_recorded()
+    d = renderer.download_kd()
+    for other in (a2, b, d):
+        assert a.nodes.tobytes() == other.nodes.tobytes() and a.tri_indices.tobytes() == other.tri_indices.tobytes()
+    _check_tree(a, exhaustive=False)
+
+
 def test_update_vertices_and_rebuild(clpt, renderer):
     """Animated scenes: moving some vertices in place and rebuilding from the device-resident mesh
     gives the tree a fresh upload of the moved mesh gives."""
