@@ -79,10 +79,9 @@ struct Triple {
 struct LevelState {
     int n_nodes, n_refs;       // this level
     int n_out, n_leaf_refs;    // wire nodes allocated / leaf references written so far
-    int nx_nodes, nx_refs, nx_leaf; // what `plan` computed for the next level
     int overflow;              // a capacity was exceeded: the build stopped, the host falls back
     int levels;                // levels that had nodes
-    int pad[7];
+    int pad[10];
 };
 __host__ __device__ inline Triple operator+(Triple a, Triple b) { return Triple{ a.l + b.l, a.r + b.r, a.f + b.f }; }
 
@@ -137,9 +136,11 @@ __global__ void scene_box_kernel(const float *__restrict__ lo, const float *__re
 }
 
 __global__ void root_kernel(const int *__restrict__ box_keys, int n_tris, int max_depth, ANode *__restrict__ nodes,
-                            int *__restrict__ ref_tri, int *__restrict__ ref_node, LevelState *__restrict__ ls) {
+                            int *__restrict__ ref_tri, int *__restrict__ ref_node, LevelState *__restrict__ ls,
+                            int *__restrict__ big_counter) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
+        *big_counter = 0; // (was the bad-mesh flag of tri_bounds, already on its way to the host)
         LevelState st = {};
         st.n_nodes = 1;
         st.n_refs = n_tris;
@@ -234,16 +235,17 @@ __device__ __forceinline__ float sah_cost(const float *ext, int ax, float left_e
 constexpr int SMALL_MAX = 8;
 
 template <int W>
-__global__ void __launch_bounds__(256)
-choose_kernel(const LevelState *__restrict__ ls, const ANode *__restrict__ nodes, const unsigned *__restrict__ hist,
-              const int *__restrict__ ref_tri, const float *__restrict__ lo, const float *__restrict__ hi, int n_tris,
-              int min_split, float ct, float ci, float empty_bonus, Decision *__restrict__ decisions) {
+__device__ __forceinline__ void choose_nodes(int block, int n_blocks, const LevelState *__restrict__ ls,
+                                             const ANode *__restrict__ nodes, unsigned *__restrict__ hist,
+                                             const int *__restrict__ ref_tri, const float *__restrict__ lo,
+                                             const float *__restrict__ hi, int n_tris, int min_split, float ct, float ci,
+                                             float empty_bonus, Decision *__restrict__ decisions) {
     const int lane = threadIdx.x & 31, sub = lane & (W - 1);
     const unsigned mask = W == 32 ? 0xffffffffu : (((1u << W) - 1u) << (lane & ~(W - 1)));
     const int n_nodes = ls->n_nodes;
-    const int groups = (int)(((size_t)gridDim.x * blockDim.x) / W);
+    const int groups = (int)(((size_t)n_blocks * blockDim.x) / W);
     // grid-stride over the nodes (whole groups move together: `a` is uniform in a group)
-    for (int a = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) / W); a < n_nodes; a += groups) {
+    for (int a = (int)(((size_t)block * blockDim.x + threadIdx.x) / W); a < n_nodes; a += groups) {
     const ANode nd = nodes[a];
     if ((W == 8) != (nd.count <= SMALL_MAX)) continue; // the other launch's node
     Decision d;
@@ -313,7 +315,7 @@ choose_kernel(const LevelState *__restrict__ ls, const ANode *__restrict__ nodes
                     }
                 }
             } else if (W == 32) {
-                const unsigned *h = hist + (size_t)nd.hist_slot * (3 * 2 * NBINS);
+                unsigned *h = hist + (size_t)nd.hist_slot * (3 * 2 * NBINS);
                 const unsigned s = h[(ax * 2 + 0) * NBINS + lane], e = h[(ax * 2 + 1) * NBINS + lane];
                 // exclusive prefix sums: plane k (k = lane, 1..31) sits at the low edge of bin k
                 unsigned ps = s, pe = e;
@@ -355,6 +357,28 @@ choose_kernel(const LevelState *__restrict__ ls, const ANode *__restrict__ nodes
         }
     }
     if (sub == 0) decisions[a] = d;
+    // the histograms are left zeroed for the next level (they are cleared once per build, not per level)
+    if (W == 32 && nd.hist_slot >= 0) {
+        unsigned *h = hist + (size_t)nd.hist_slot * (3 * 2 * NBINS);
+#pragma unroll
+        for (int k = 0; k < 3 * 2; k++) h[k * NBINS + lane] = 0u;
+    }
+    }
+}
+
+// One launch for both widths: the first `blocks32` blocks serve the nodes of more than SMALL_MAX
+// references, the rest the small ones.
+__global__ void __launch_bounds__(256)
+choose_kernel(int blocks32, const LevelState *__restrict__ ls, const ANode *__restrict__ nodes,
+              unsigned *__restrict__ hist, const int *__restrict__ ref_tri, const float *__restrict__ lo,
+              const float *__restrict__ hi, int n_tris, int min_split, float ct, float ci, float empty_bonus,
+              Decision *__restrict__ decisions) {
+    if ((int)blockIdx.x < blocks32) {
+        choose_nodes<32>((int)blockIdx.x, blocks32, ls, nodes, hist, ref_tri, lo, hi, n_tris, min_split, ct, ci,
+                         empty_bonus, decisions);
+    } else {
+        choose_nodes<8>((int)blockIdx.x - blocks32, (int)gridDim.x - blocks32, ls, nodes, hist, ref_tri, lo, hi, n_tris,
+                        min_split, ct, ci, empty_bonus, decisions);
     }
 }
 
@@ -376,12 +400,12 @@ __device__ __forceinline__ Triple ref_flags(const ANode *__restrict__ nodes, con
     return Triple{ left ? 1u : 0u, right ? 1u : 0u, 0u };
 }
 
+// Two sequences are scanned by every launch (the references and the nodes of a level: both
+// depend on the decisions only): blocks [0, tiles_a) serve sequence A, the rest sequence B.
 template <typename F>
-__global__ void __launch_bounds__(SCAN_BLOCK) scan_tile_sums_kernel(const int *__restrict__ n_ptr, F f,
-                                                                     Triple *__restrict__ tile_sums) {
+__device__ __forceinline__ void scan_tile_sums(int tile, int n, const F &f, Triple *__restrict__ tile_sums) {
     __shared__ Triple warp_sums[SCAN_BLOCK / 32];
-    const int n = *n_ptr;
-    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     Triple s = { 0u, 0u, 0u };
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
@@ -397,15 +421,26 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_tile_sums_kernel(const int *_
     if (threadIdx.x == 0) {
         Triple t = { 0u, 0u, 0u };
         for (int w = 0; w < SCAN_BLOCK / 32; w++) t = t + warp_sums[w];
-        tile_sums[blockIdx.x] = t;
+        tile_sums[tile] = t;
     }
 }
 
-// Exclusive scan of the tile sums in place, one block; the grand total lands in total[0].
-__global__ void __launch_bounds__(1024) scan_tile_offsets_kernel(Triple *__restrict__ tile_sums, int n_tiles,
+template <typename FA, typename FB>
+__global__ void __launch_bounds__(SCAN_BLOCK)
+scan_tile_sums_kernel(int tiles_a, const int *__restrict__ na, FA fa, Triple *__restrict__ sums_a,
+                      const int *__restrict__ nb, FB fb, Triple *__restrict__ sums_b) {
+    if ((int)blockIdx.x < tiles_a) scan_tile_sums((int)blockIdx.x, *na, fa, sums_a);
+    else scan_tile_sums((int)blockIdx.x - tiles_a, *nb, fb, sums_b);
+}
+
+// Exclusive scan of the tile sums in place, one block per sequence; the grand totals land in total[0] (A), total[1] (B).
+__global__ void __launch_bounds__(1024) scan_tile_offsets_kernel(Triple *__restrict__ sums_a, int tiles_a,
+                                                                 Triple *__restrict__ sums_b, int tiles_b,
                                                                  Triple *__restrict__ total) {
     __shared__ Triple warp_sums[32];
     __shared__ Triple carry;
+    Triple *tile_sums = blockIdx.x == 0 ? sums_a : sums_b;
+    const int n_tiles = blockIdx.x == 0 ? tiles_a : tiles_b;
     if (threadIdx.x == 0) carry = Triple{ 0u, 0u, 0u };
     __syncthreads();
     for (int base = 0; base < n_tiles; base += 1024) {
@@ -426,18 +461,15 @@ __global__ void __launch_bounds__(1024) scan_tile_offsets_kernel(Triple *__restr
         if (threadIdx.x == 1023) carry = Triple{ before.l + s.l, before.r + s.r, before.f + s.f };
         __syncthreads();
     }
-    if (threadIdx.x == 0) total[0] = carry;
+    if (threadIdx.x == 0) total[blockIdx.x] = carry;
 }
 
 // Exclusive scan values for every item (plus one past the end = totals).
 template <typename F>
-__global__ void __launch_bounds__(SCAN_BLOCK) scan_write_kernel(const int *__restrict__ n_ptr, F f,
-                                                                const Triple *__restrict__ tile_offsets,
-                                                                const Triple *__restrict__ total,
-                                                                Triple *__restrict__ out /* n + 1 */) {
+__device__ __forceinline__ void scan_write(int tile, int n, const F &f, const Triple *__restrict__ tile_offsets,
+                                           const Triple *__restrict__ total, Triple *__restrict__ out /* n + 1 */) {
     __shared__ Triple warp_sums[SCAN_BLOCK / 32];
-    const int n = *n_ptr;
-    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     Triple v[SCAN_ITEMS];
     Triple s = { 0u, 0u, 0u };
 #pragma unroll
@@ -453,7 +485,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_write_kernel(const int *__res
     }
     if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = inc;
     __syncthreads();
-    Triple before = tile_offsets[blockIdx.x];
+    Triple before = tile_offsets[tile];
     for (int w = 0; w < (int)(threadIdx.x >> 5); w++) before = before + warp_sums[w];
     Triple run = Triple{ before.l + inc.l - s.l, before.r + inc.r - s.r, before.f + inc.f - s.f };
 #pragma unroll
@@ -461,8 +493,21 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_write_kernel(const int *__res
         if (base + k < n) out[base + k] = run;
         run = run + v[k];
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = total[0];
+    if (tile == 0 && threadIdx.x == 0) out[n] = total[0];
 }
+
+template <typename FA, typename FB>
+__global__ void __launch_bounds__(SCAN_BLOCK)
+scan_write_kernel(int tiles_a, const int *__restrict__ na, FA fa, const Triple *__restrict__ offsets_a,
+                  Triple *__restrict__ out_a, const int *__restrict__ nb, FB fb, const Triple *__restrict__ offsets_b,
+                  Triple *__restrict__ out_b, const Triple *__restrict__ total) {
+    if ((int)blockIdx.x < tiles_a) scan_write((int)blockIdx.x, *na, fa, offsets_a, total, out_a);
+    else scan_write((int)blockIdx.x - tiles_a, *nb, fb, offsets_b, total + 1, out_b);
+}
+
+struct NoItemsFn { // the empty second sequence of a single scan
+    __device__ Triple operator()(int) const { return Triple{ 0u, 0u, 0u }; }
+};
 
 struct RefFlagFn {
     const ANode *nodes;
@@ -492,11 +537,26 @@ __device__ __forceinline__ void write_box(int *__restrict__ wire, int out, const
     w[7] = 0;
 }
 
-__global__ void emit_kernel(const LevelState *__restrict__ ls, const ANode *__restrict__ nodes,
-                            const Decision *__restrict__ dec, const Triple *__restrict__ node_scan /* n_nodes + 1 */,
-                            const Triple *__restrict__ ref_scan /* n_refs + 1 */, int *__restrict__ wire,
-                            ANode *__restrict__ next_nodes, int *__restrict__ big_counter) {
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+// Room in the buffers a level's split writes.  Every thread of the split checks the level's
+// totals against it (a few broadcast loads) and leaves the level alone when it does not fit;
+// `commit` then stops the build and tells the host, which starts over level by level with
+// every buffer sized exactly.
+struct Room {
+    int nodes_next, refs, out, leaf;
+};
+
+__device__ __forceinline__ bool level_fits(const LevelState *__restrict__ ls, const Triple *__restrict__ totals,
+                                           const Room &room) {
+    const long long nx_nodes = 2ll * totals[1].l, nx_refs = (long long)totals[0].l + totals[0].r, nx_leaf = totals[0].f;
+    return ls->n_out + nx_nodes <= room.out && ls->n_leaf_refs + nx_leaf <= room.leaf && nx_refs <= room.refs &&
+           nx_nodes <= room.nodes_next;
+}
+
+__device__ __forceinline__ void emit_node(int a, const LevelState *__restrict__ ls, const ANode *__restrict__ nodes,
+                                          const Decision *__restrict__ dec,
+                                          const Triple *__restrict__ node_scan /* n_nodes + 1 */,
+                                          const Triple *__restrict__ ref_scan /* n_refs + 1 */, int *__restrict__ wire,
+                                          ANode *__restrict__ next_nodes, int *__restrict__ big_counter) {
     if (a >= ls->n_nodes) return;
     const int next_out_base = ls->n_out, leaf_ref_base = ls->n_leaf_refs;
     const ANode nd = nodes[a];
@@ -539,13 +599,12 @@ __global__ void emit_kernel(const LevelState *__restrict__ ls, const ANode *__re
     next_nodes[2 * rank + 1] = R;
 }
 
-__global__ void scatter_kernel(const ANode *__restrict__ nodes, const Decision *__restrict__ dec,
-                               const Triple *__restrict__ node_scan, const Triple *__restrict__ ref_scan,
-                               const int *__restrict__ ref_tri, const int *__restrict__ ref_node,
-                               const LevelState *__restrict__ ls, const float *__restrict__ lo,
-                               const float *__restrict__ hi, int n_tris, int *__restrict__ next_tri,
-                               int *__restrict__ next_node, int *__restrict__ tri_indices) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void scatter_ref(int i, const ANode *__restrict__ nodes, const Decision *__restrict__ dec,
+                                            const Triple *__restrict__ node_scan, const Triple *__restrict__ ref_scan,
+                                            const int *__restrict__ ref_tri, const int *__restrict__ ref_node,
+                                            const LevelState *__restrict__ ls, const float *__restrict__ lo,
+                                            const float *__restrict__ hi, int n_tris, int *__restrict__ next_tri,
+                                            int *__restrict__ next_node, int *__restrict__ tri_indices) {
     if (i >= ls->n_refs) return;
     const int leaf_ref_base = ls->n_leaf_refs;
     const int a = ref_node[i], t = ref_tri[i];
@@ -571,34 +630,49 @@ __global__ void scatter_kernel(const ANode *__restrict__ nodes, const Decision *
     }
 }
 
-// ---- level bookkeeping on the device ------------------------------------------------------
-// After the scans: what the next level will hold, checked against the capacities of the buffers
-// the level's emit and scatter are about to write.  Over capacity -> the build stops here (this
-// level and all later ones become empty) and `overflow` tells the host, which falls back to the
-// path that sizes every level exactly.
-__global__ void plan_kernel(LevelState *__restrict__ ls, const Triple *__restrict__ ref_total,
-                            const Triple *__restrict__ node_total, int cap_nodes_next, int cap_refs, int cap_out,
-                            int cap_leaf) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    long long nx_nodes = 2ll * node_total->l, nx_refs = (long long)ref_total->l + ref_total->r, nx_leaf = ref_total->f;
-    if (ls->n_nodes > 0) ls->levels++;
-    if (ls->n_out + nx_nodes > cap_out || ls->n_leaf_refs + nx_leaf > cap_leaf || nx_refs > cap_refs ||
-        nx_nodes > cap_nodes_next) {
-        ls->overflow = 1;
-        ls->n_nodes = ls->n_refs = 0;
-        nx_nodes = nx_refs = nx_leaf = 0;
+// The split of a level in one launch: blocks [0, emit_blocks) write the wire nodes and the
+// next level's nodes (one thread per node), the rest move the references (one thread each).
+struct SplitArgs {
+    const ANode *nodes;
+    const Decision *dec;
+    const Triple *node_scan, *ref_scan, *totals;
+    const int *ref_tri, *ref_node;
+    const float *lo, *hi;
+    int n_tris;
+    int *wire;
+    ANode *next_nodes;
+    int *big_counter, *next_tri, *next_node, *tri_indices;
+    Room room;
+};
+
+__global__ void split_kernel(int emit_blocks, const LevelState *__restrict__ ls, const SplitArgs A) {
+    if (!level_fits(ls, A.totals, A.room)) return;
+    if ((int)blockIdx.x < emit_blocks) {
+        emit_node((int)(blockIdx.x * blockDim.x + threadIdx.x), ls, A.nodes, A.dec, A.node_scan, A.ref_scan, A.wire,
+                  A.next_nodes, A.big_counter);
+    } else {
+        scatter_ref((int)((blockIdx.x - emit_blocks) * blockDim.x + threadIdx.x), A.nodes, A.dec, A.node_scan, A.ref_scan,
+                    A.ref_tri, A.ref_node, ls, A.lo, A.hi, A.n_tris, A.next_tri, A.next_node, A.tri_indices);
     }
-    ls->nx_nodes = (int)nx_nodes;
-    ls->nx_refs = (int)nx_refs;
-    ls->nx_leaf = (int)nx_leaf;
 }
 
-__global__ void commit_kernel(LevelState *__restrict__ ls) {
+// ---- level bookkeeping on the device ------------------------------------------------------
+// After the split: the level state moves on to the next level (or the build stops, see Room).
+__global__ void commit_kernel(LevelState *__restrict__ ls, const Triple *__restrict__ totals, const Room room,
+                              int *__restrict__ big_counter) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    ls->n_out += ls->nx_nodes;
-    ls->n_leaf_refs += ls->nx_leaf;
-    ls->n_nodes = ls->nx_nodes;
-    ls->n_refs = ls->nx_refs;
+    *big_counter = 0; // the histogram slots of the next level are handed out from 0 again
+    if (ls->n_nodes > 0) ls->levels++;
+    if (!level_fits(ls, totals, room)) {
+        ls->overflow = 1;
+        ls->n_nodes = ls->n_refs = 0;
+        return;
+    }
+    const int nx_nodes = 2 * (int)totals[1].l;
+    ls->n_out += nx_nodes;
+    ls->n_leaf_refs += (int)totals[0].f;
+    ls->n_nodes = nx_nodes;
+    ls->n_refs = (int)(totals[0].l + totals[0].r);
 }
 
 // ---- ropes -----------------------------------------------------------------------------
@@ -695,16 +769,19 @@ void drop_graph() {
     W.graph = nullptr;
 }
 
-// Scan of f(0..n-1), n read from device memory; `n_cap` (>= n) sizes the launch.
-template <typename F>
-void scan(const int *n_ptr, int n_cap, F f, Triple *out, Triple *total_dev, cudaStream_t s) {
-    const int tiles = std::max(1, (n_cap + SCAN_TILE - 1) / SCAN_TILE);
-    scan_tile_sums_kernel<<<tiles, SCAN_BLOCK, 0, s>>>(n_ptr, f, W.tiles);
-    scan_tile_offsets_kernel<<<1, 1024, 0, s>>>(W.tiles, tiles, total_dev);
-    scan_write_kernel<<<tiles, SCAN_BLOCK, 0, s>>>(n_ptr, f, W.tiles, total_dev, out);
-}
-
 int scan_tiles(size_t n_cap) { return (int)std::max<size_t>(1, (n_cap + SCAN_TILE - 1) / SCAN_TILE); }
+
+// Two scans in three launches (see scan_tile_sums_kernel): f(0..na-1) and g(0..nb-1), the counts read
+// from device memory; `cap_a`, `cap_b` (>= the counts) size the launches.  Totals land in total_dev[0], [1].
+template <typename FA, typename FB>
+void scan2(const int *na, size_t cap_a, FA fa, Triple *out_a, const int *nb, size_t cap_b, FB fb, Triple *out_b,
+           Triple *total_dev, cudaStream_t s) {
+    const int ta = scan_tiles(cap_a), tb = scan_tiles(cap_b);
+    Triple *sums_a = W.tiles, *sums_b = W.tiles + ta;
+    scan_tile_sums_kernel<<<ta + tb, SCAN_BLOCK, 0, s>>>(ta, na, fa, sums_a, nb, fb, sums_b);
+    scan_tile_offsets_kernel<<<2, 1024, 0, s>>>(sums_a, ta, sums_b, tb, total_dev);
+    scan_write_kernel<<<ta + tb, SCAN_BLOCK, 0, s>>>(ta, na, fa, sums_a, out_a, nb, fb, sums_b, out_b, total_dev);
+}
 
 constexpr int T = 256;
 constexpr int CHOOSE_MAX_BLOCKS = 148 * 16;
@@ -724,48 +801,45 @@ void enqueue_prologue(const BuildArgs &A, cudaStream_t s) {
     scene_box_kernel<<<std::min(1024, (A.n_tris + T - 1) / T), T, 0, s>>>(W.lo, W.hi, A.n_tris, W.box_keys);
     CU(cudaMemcpyAsync(&W.host->bad, W.bad, sizeof(int), cudaMemcpyDeviceToHost, s));
     root_kernel<<<(A.n_tris + T - 1) / T, T, 0, s>>>(W.box_keys, A.n_tris, A.max_depth, W.nodes[0], W.ref_tri[0],
-                                                     W.ref_node[0], W.level);
+                                                     W.ref_node[0], W.level, W.bad);
+}
+
+size_t hist_words(size_t refs) { // nodes with histograms hold more than EXACT_MAX references
+    return (refs / (EXACT_MAX + 1) + 1) * 3 * 2 * NBINS;
 }
 
 // The first half of a level: histograms, the split decisions, the two scans.  `refs` and
 // `nodes` size the launches (the true counts, or upper bounds -- the kernels read the true
-// counts from the level state).
+// counts from the level state).  The histograms must be zero on entry and are zero on exit.
 void enqueue_decide(const BuildArgs &A, int cur, size_t refs, size_t nodes, cudaStream_t s) {
     const LevelState *ls = W.level;
-    const size_t hist_slots = refs / (EXACT_MAX + 1) + 1; // nodes with histograms hold more than EXACT_MAX references
-    CU(cudaMemsetAsync(W.hist, 0, hist_slots * 3 * 2 * NBINS * sizeof(unsigned), s));
     if (refs > 0) {
         bin_kernel<<<(unsigned)((refs + 255) / 256), 256, 0, s>>>(ls, W.nodes[cur], W.ref_tri[cur], W.ref_node[cur], W.lo,
                                                                   W.hi, A.n_tris, A.min_split, W.hist);
     }
-    const unsigned g32 = (unsigned)std::min<size_t>(CHOOSE_MAX_BLOCKS, (nodes * 32 + 255) / 256);
-    const unsigned g8 = (unsigned)std::min<size_t>(CHOOSE_MAX_BLOCKS, (nodes * 8 + 255) / 256);
-    choose_kernel<32><<<std::max(1u, g32), 256, 0, s>>>(ls, W.nodes[cur], W.hist, W.ref_tri[cur], W.lo, W.hi, A.n_tris,
-                                                        A.min_split, A.ct, A.ci, A.empty_bonus, W.dec);
-    choose_kernel<8><<<std::max(1u, g8), 256, 0, s>>>(ls, W.nodes[cur], W.hist, W.ref_tri[cur], W.lo, W.hi, A.n_tris,
-                                                      A.min_split, A.ct, A.ci, A.empty_bonus, W.dec);
+    // nodes of more than SMALL_MAX references: there are at most refs / SMALL_MAX of them
+    const size_t big = std::min(nodes, refs / SMALL_MAX + 1);
+    const int g32 = (int)std::max<size_t>(1, std::min<size_t>(CHOOSE_MAX_BLOCKS, (big * 32 + 255) / 256));
+    const int g8 = (int)std::max<size_t>(1, std::min<size_t>(CHOOSE_MAX_BLOCKS, (nodes * 8 + 255) / 256));
+    choose_kernel<<<g32 + g8, 256, 0, s>>>(g32, ls, W.nodes[cur], W.hist, W.ref_tri[cur], W.lo, W.hi, A.n_tris,
+                                           A.min_split, A.ct, A.ci, A.empty_bonus, W.dec);
     RefFlagFn rf{ W.nodes[cur], W.dec, W.ref_tri[cur], W.ref_node[cur], W.lo, W.hi, A.n_tris };
-    scan(&ls->n_refs, (int)refs, rf, W.ref_scan, W.totals, s);
     SplitFlagFn sf{ W.dec };
-    scan(&ls->n_nodes, (int)nodes, sf, W.node_scan, W.totals + 1, s);
+    scan2(&ls->n_refs, refs, rf, W.ref_scan, &ls->n_nodes, nodes, sf, W.node_scan, W.totals, s);
 }
 
-// The second half: capacities checked on the device, wire nodes and the next level's nodes
-// written, references moved to their children or to the leaf lists, the level state advanced.
-void enqueue_split(const BuildArgs &A, int cur, size_t refs, size_t nodes, int cap_nodes_next, int cap_refs, int cap_out,
-                   int cap_leaf, ClptGpuTree &out, cudaStream_t s) {
+// The second half: wire nodes and the next level's nodes written, references moved to their
+// children or to the leaf lists (all of it only if the level fits `room`), the level state advanced.
+void enqueue_split(const BuildArgs &A, int cur, size_t refs, size_t nodes, const Room &room, ClptGpuTree &out,
+                   cudaStream_t s) {
     const int nxt = cur ^ 1;
-    plan_kernel<<<1, 32, 0, s>>>(W.level, W.totals, W.totals + 1, cap_nodes_next, cap_refs, cap_out, cap_leaf);
-    CU(cudaMemsetAsync(W.bad, 0, sizeof(int), s)); // doubles as the histogram-slot counter of the next level
-    emit_kernel<<<(unsigned)std::max<size_t>(1, (nodes + T - 1) / T), T, 0, s>>>(W.level, W.nodes[cur], W.dec, W.node_scan,
-                                                                                 W.ref_scan, out.wire, W.nodes[nxt], W.bad);
-    if (refs > 0) {
-        scatter_kernel<<<(unsigned)((refs + T - 1) / T), T, 0, s>>>(W.nodes[cur], W.dec, W.node_scan, W.ref_scan,
-                                                                    W.ref_tri[cur], W.ref_node[cur], W.level, W.lo, W.hi,
-                                                                    A.n_tris, W.ref_tri[nxt], W.ref_node[nxt],
-                                                                    out.tri_indices);
-    }
-    commit_kernel<<<1, 32, 0, s>>>(W.level);
+    SplitArgs sa = { W.nodes[cur], W.dec,        W.node_scan,   W.ref_scan,    W.totals,        W.ref_tri[cur],
+                     W.ref_node[cur], W.lo,      W.hi,          A.n_tris,      out.wire,        W.nodes[nxt],
+                     W.bad,        W.ref_tri[nxt], W.ref_node[nxt], out.tri_indices, room };
+    const int emit_blocks = (int)std::max<size_t>(1, (nodes + T - 1) / T);
+    const int scatter_blocks = (int)((refs + T - 1) / T);
+    split_kernel<<<emit_blocks + scatter_blocks, T, 0, s>>>(emit_blocks, W.level, sa);
+    commit_kernel<<<1, 32, 0, s>>>(W.level, W.totals, room, W.bad);
 }
 
 // Meshes up to this size are built without the host in the loop (below).
@@ -791,10 +865,11 @@ bool build_recorded(const BuildArgs &A, int room_pc, ClptGpuTree &out, cudaStrea
         ensure(W.nodes[k], W.node_cap[k], cap_nodes);
     }
     ensure(W.dec, W.dec_cap, cap_nodes);
-    ensure(W.hist, W.hist_cap, (cap_refs / (EXACT_MAX + 1) + 1) * 3 * 2 * NBINS);
+    ensure(W.hist, W.hist_cap, hist_words(cap_refs));
     ensure(W.ref_scan, W.ref_scan_cap, cap_refs + 1);
     ensure(W.node_scan, W.node_scan_cap, cap_nodes + 1);
-    ensure(W.tiles, W.tiles_cap, (size_t)scan_tiles(cap_out)); // (also what the re-layout of this tree will ask for)
+    // (the second term: what the re-layout of this tree will ask for)
+    ensure(W.tiles, W.tiles_cap, (size_t)std::max(scan_tiles(cap_refs) + scan_tiles(cap_nodes), scan_tiles(cap_out) + 1));
     ensure(out.wire, out.wire_cap, cap_out * 17);
     ensure(out.tri_indices, out.tri_indices_cap, cap_leaf);
     const Workspace::GraphKey key = { A.verts, A.corners, out.wire, out.tri_indices, g_reallocations, cap_refs, A.n_verts, A.n_tris,
@@ -803,6 +878,7 @@ bool build_recorded(const BuildArgs &A, int room_pc, ClptGpuTree &out, cudaStrea
         drop_graph();
         cudaGraph_t g = nullptr;
         CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        CU(cudaMemsetAsync(W.hist, 0, hist_words(cap_refs) * sizeof(unsigned), s)); // (each level leaves it zeroed)
         enqueue_prologue(A, s);
         int cur = 0;
         for (int level = 0; level <= A.max_depth; level++) {
@@ -811,7 +887,7 @@ bool build_recorded(const BuildArgs &A, int room_pc, ClptGpuTree &out, cudaStrea
             const size_t nodes_next = level + 1 < 30 ? std::min<size_t>(cap_nodes, (size_t)2 << level) : cap_nodes;
             const size_t refs = level == 0 ? n : cap_refs;
             enqueue_decide(A, cur, refs, nodes, s);
-            enqueue_split(A, cur, refs, nodes, (int)nodes_next, (int)cap_refs, (int)cap_out, (int)cap_leaf, out, s);
+            enqueue_split(A, cur, refs, nodes, Room{ (int)nodes_next, (int)cap_refs, (int)cap_out, (int)cap_leaf }, out, s);
             cur ^= 1;
         }
         push_ropes_kernel<<<(unsigned)((cap_out * 6 + T - 1) / T), T, 0, s>>>(out.wire, W.level);
@@ -894,10 +970,12 @@ bool clpt_gpu_build(const float4 *verts, int n_verts, const int4 *corners, int n
     while (n_nodes > 0) {
         levels++;
         ensure(W.dec, W.dec_cap, n_nodes);
-        ensure(W.hist, W.hist_cap, (n_refs / (EXACT_MAX + 1) + 1) * 3 * 2 * NBINS);
+        ensure(W.hist, W.hist_cap, hist_words(n_refs));
         ensure(W.ref_scan, W.ref_scan_cap, n_refs + 1);
         ensure(W.node_scan, W.node_scan_cap, n_nodes + 1);
-        ensure(W.tiles, W.tiles_cap, (size_t)scan_tiles(std::max(n_refs, n_nodes)));
+        ensure(W.tiles, W.tiles_cap, (size_t)(scan_tiles(n_refs) + scan_tiles(n_nodes)));
+        // (the buffer may just have moved; otherwise the previous level left it zeroed and this is redundant)
+        CU(cudaMemsetAsync(W.hist, 0, hist_words(n_refs) * sizeof(unsigned), s));
         enqueue_decide(A, cur, n_refs, n_nodes, s);
         CU(cudaMemcpyAsync(W.host->totals, W.totals, 2 * sizeof(Triple), cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
@@ -938,7 +1016,7 @@ bool clpt_gpu_build(const float4 *verts, int n_verts, const int4 *corners, int n
         ensure(W.ref_tri[nxt], W.ref_cap[nxt][0], next_refs);
         ensure(W.ref_node[nxt], W.ref_cap[nxt][1], next_refs);
         ensure(W.nodes[nxt], W.node_cap[nxt], next_nodes);
-        enqueue_split(A, cur, n_refs, n_nodes, INT_MAX, INT_MAX, INT_MAX, INT_MAX, out, s);
+        enqueue_split(A, cur, n_refs, n_nodes, Room{ INT_MAX, INT_MAX, INT_MAX, INT_MAX }, out, s);
         n_out += next_nodes;
         n_leaf_refs += rt.f;
         n_nodes = next_nodes;
@@ -1091,13 +1169,16 @@ bool clpt_gpu_pack(const ClptGpuTree &tree, const float4 *verts, const int4 *cor
     }
     ensure_host();
     ensure(g_new_of, g_new_of_cap, (size_t)n);
-    ensure(g_wire_scan, g_wire_scan_cap, (size_t)n + 1);
-    ensure(W.tiles, W.tiles_cap, (size_t)scan_tiles((size_t)n));
+    ensure(g_wire_scan, g_wire_scan_cap, (size_t)n + 2);
+    ensure(W.tiles, W.tiles_cap, (size_t)scan_tiles((size_t)n) + 1);
     W.host->n = n;
     int *n_dev = &W.level[1].n_nodes;
     CU(cudaMemcpyAsync(n_dev, &W.host->n, sizeof(int), cudaMemcpyHostToDevice, s));
     WireTypeFn tf{ tree.wire };
-    scan(n_dev, n, tf, g_wire_scan, W.totals, s);
+    int *zero_dev = &W.level[1].n_refs; // (an empty second sequence)
+    CU(cudaMemsetAsync(zero_dev, 0, sizeof(int), s));
+    scan2(n_dev, (size_t)n, tf, g_wire_scan, zero_dev, 0, NoItemsFn{}, g_wire_scan /* one word past the first */ + n + 1,
+          W.totals, s);
     CU(cudaMemcpyAsync(W.host->totals, W.totals, sizeof(Triple), cudaMemcpyDeviceToHost, s));
     float box[8];
     CU(cudaMemcpyAsync(box, tree.wire, sizeof(box), cudaMemcpyDeviceToHost, s));
