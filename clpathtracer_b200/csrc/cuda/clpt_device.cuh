@@ -122,6 +122,7 @@ enum { CLPT_F_JITTER = 1, CLPT_F_ACCUMULATE = 2, CLPT_F_COUNTERS = 4, CLPT_F_REV
 
 // render_kernel.cu
 void clpt_launch_render(const ClptScene &scene, const ClptFrame &frame, int sm_count, cudaStream_t stream);
+int clpt_render_blocks_per_sm(int engine);          // resident 256-thread blocks per SM the render kernel is compiled for
 int clpt_render_block_rows(const ClptFrame &frame); // rows of blocks the launch will walk (size of row_cost)
 void clpt_launch_deinterleave(const float4 *gathered, float4 *image, int width, int height,
                               int nranks, int tile_rows, int slab_rows, cudaStream_t stream);

@@ -273,11 +273,13 @@ __device__ __forceinline__ bool hit_is_final(int ref, float tmin, float min_hit)
 // (:384); true when the ray leaves the scene or exhausts its rope-hop budget.
 template <bool COUNT>
 __device__ __forceinline__ bool leave_leaf(const uint2 *__restrict__ nodes, const float4 *L, int far, V3 o, V3 d,
-                                           float tmax, int max_visits, V3 &p1, uint2 &n, int &visits, Counters &cn) {
+                                           float tmax, V3 &p1, uint2 &n, int &visits_left, Counters &cn) {
     p1 = vadd(o, vscale(d, tmax));
     const int next = __ldg(reinterpret_cast<const int *>(L + 2) + far);
     if (next == -1) return true;
-    if (++visits >= max_visits) {
+    // the rope-hop budget counts DOWN: one live value and one add + test per leaf, where counting up
+    // against max_visits had the bound re-derived from constant memory at every leaf
+    if (--visits_left <= 0) {
         if (COUNT) cn.capped++;
         return true;
     }
@@ -303,7 +305,7 @@ __device__ __forceinline__ Hit closest_hit(const ClptScene &S, V3 o, V3 d, int m
     V3 p1 = o;
     if (tmin > 0.0f) p1 = vadd(p1, vscale(d, tmin));
 
-    int visits = 0;
+    int visits_left = max_visits > 1 ? max_visits : 1; // (the budget ends the walk at hop max(max_visits, 1))
     float min_hit = 0.0f;
     const uint2 *__restrict__ nodes = S.nodes;
     // the instrumented twin walks from the root so that its counters are the
@@ -330,7 +332,7 @@ __device__ __forceinline__ Hit closest_hit(const ClptScene &S, V3 o, V3 d, int m
         }
         // (the box is re-read from L1 rather than kept live across the run)
         if (h.ref >= 0 && hit_is_final(h.ref, leaf_entry(__ldg(L), __ldg(L + 1), o, inv), min_hit)) break;
-        if (leave_leaf<COUNT>(nodes, L, far, o, d, tmax, max_visits, p1, n, visits, cn)) break;
+        if (leave_leaf<COUNT>(nodes, L, far, o, d, tmax, p1, n, visits_left, cn)) break;
     }
     h.t = min_hit;
     return h;

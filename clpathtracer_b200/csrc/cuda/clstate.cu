@@ -790,6 +790,19 @@ void clpt_state_launch_frame(int width, int height) {
         if (getenv("CLPT_VERBOSE") && atoi(getenv("CLPT_VERBOSE")) >= 3) {
             fprintf(stderr, "CLExecute: costliest rows at %.2f of %d, next frame claims %s\n", where, order_rows,
                     St.claim_reverse ? "bottom-up" : "top-down");
+            {   // how much of the resident warps' time was spent inside claims (the rest: the frame's tail)
+                unsigned long long in_claims = 0, longest = 0;
+                for (int r = 0; r < order_rows; r++) {
+                    in_claims += St.host_row_cost[r];
+                    if (St.host_row_cost[order_rows + r] > longest) longest = St.host_row_cost[order_rows + r];
+                }
+                const int per_sm = clpt_render_blocks_per_sm(St.last_engine);
+                const double groups = (double)St.prop.multiProcessorCount * per_sm * (8 >> F.log2_warps_per_pixel);
+                const double clocks = (double)St.last_kernel_ms * 1e-3 * (double)St.prop.clockRate * 1e3;
+                fprintf(stderr, "CLExecute: %.3f ms; claims fill %.1f%% of the resident warp groups' time (at %d MHz); "
+                                "longest claim %.3f ms\n", St.last_kernel_ms, 100.0 * (double)in_claims / (groups * clocks),
+                        St.prop.clockRate / 1000, (double)longest / ((double)St.prop.clockRate * 1e3) * 1e3);
+            }
             if (atoi(getenv("CLPT_VERBOSE")) >= 4) {
                 for (int r = 0; r < order_rows; r++) {
                     fprintf(stderr, "  row %d: claims %llu kclk in all, longest %llu kclk\n", r,

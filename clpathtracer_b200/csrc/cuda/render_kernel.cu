@@ -371,6 +371,8 @@ int clpt_render_block_rows(const ClptFrame &frame) {
     return (frame.local_rows + block_h - 1) / block_h;
 }
 
+int clpt_render_blocks_per_sm(int engine) { return engine == 2 ? CLPT_FAT_MIN_BLOCKS : CLPT_MIN_BLOCKS; }
+
 void clpt_launch_render(const ClptScene &scene, const ClptFrame &frame_in, int sm_count, cudaStream_t stream) {
     ClptFrame frame = frame_in;
     if (!(frame.flags & CLPT_F_FAT)) frame.log2_lanes_per_ray = 0;
