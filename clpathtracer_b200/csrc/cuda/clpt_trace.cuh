@@ -21,9 +21,9 @@
 
 #ifndef CLPT_FAT_MIN_BLOCKS
 // Engine 2, for trees with fat leaves (the reference builder's DEPTH-15 trees: ~56 triangles per
-// leaf at 1M triangles): the same code compiled for fewer resident blocks.  Such frames are short
-// and end with a few warps walking the grazing rays of the horizon (thousands of triangle tests
-// each), so what counts is how fast ONE warp runs, not how many are resident (measured,
+// leaf at 1M triangles): the same code compiled for fewer resident blocks.  Such a frame is one long
+// triangle loop, which spills at 32 registers and does not at 64; the 32 warps then resident still
+// keep the issue slots 62% busy (measured: 3 blocks 3.01 ms, 4 2.86, 5 4.13, 8 3.76;
 // profiles/r02_experiments.json).
 #define CLPT_FAT_MIN_BLOCKS 4
 #endif
@@ -219,14 +219,14 @@ __device__ __forceinline__ void triangle_run(const float4 *__restrict__ tri, int
 }
 
 // ---- several lanes per ray (engine 2, one sample per pixel) -------------------------------
-// On a reference-built tree a leaf holds ~56 triangles and a grazing ray tests thousands; with one
-// lane per ray a frame ends on a handful of warps walking such rays (ncu: 47% of the warp slots
-// occupied on average).  Here K neighbouring lanes walk the SAME ray -- the descent and the leaf
-// steps are done redundantly (identical control flow, broadcast loads) -- and share a leaf's
-// triangle run: lane j tests triangles j, j+K, j+2K, ...  A warp tile is then 32/K pixels: K
-// times as many claims, each 1/K as long.  Measured on the 1M-triangle reference tree (as
-// shipped, 1080p): K = 1 3.00 ms, K = 2 2.63 ms, K = 4 2.87 ms (the redundant walk starts to
-// cost more than the shorter tail saves), so K = 2 is used.
+// On a reference-built tree a leaf holds ~56 triangles and a grazing ray tests thousands.  Here K
+// neighbouring lanes walk the SAME ray -- the descent and the leaf steps are done redundantly
+// (identical control flow, broadcast loads) -- and share a leaf's triangle run: lane j tests
+// triangles j, j+K, j+2K, ...  A warp tile is then 32/K pixels: fewer distinct leaves per warp (the
+// run's trip count is the longest among the lanes), K times as many claims, each 1/K as long.
+// Measured on the 1M-triangle reference tree (as shipped, 1080p): K = 1 3.00 ms, K = 2 2.63 ms,
+// K = 4 2.87, 8 3.39, 16 4.77, 32 7.59 (the redundant walk costs more than the shorter runs save),
+// so K = 2 is used.  (Not a tail effect: the claims fill 96% of the resident warps' time.)
 // Combining the K partial results reproduces the serial loop exactly: the smallest t wins; among
 // equal t a triangle accepted in THIS leaf beats the hit carried in from earlier leaves
 // (`t <= minHit`, src/kernel.cl:344) and the later triangle beats the earlier.

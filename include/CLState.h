@@ -160,10 +160,10 @@ void CLSetMaxLeafVisits(int cap);          /* rope-hop cap per ray; default 4096
  * registers), the fastest on deep trees where latency hiding decides; 2 = the same
  * code compiled for 4 (64 registers, no spills) -- made for trees from the
  * reference's own builder, whose DEPTH 15 cap (src/kd_tree.c:8-9) leaves ~56
- * triangles per leaf at 1M triangles: their frames end with a few warps walking
- * thousands of triangles, and a warp runs faster when fewer are resident (at one
- * sample per pixel two neighbouring lanes also walk each ray together and split
- * its leaves' triangle runs);
+ * triangles per leaf at 1M triangles: their frames are one long triangle loop,
+ * which spills at 32 registers and does not at 64 (at one sample per pixel two
+ * neighbouring lanes also walk each ray together and split its leaves' triangle
+ * runs);
  * 0 = automatic: chosen per tree at CLSetMeshes (2 when most triangle slots sit in
  * leaves of >= 8 triangles).  Both produce the same bits. */
 void CLSetEngine(int engine);
