@@ -171,7 +171,7 @@ class ClockSampler(threading.Thread):
                 for bit, name in self.REASONS.items():
                     if mask & bit:
                         self.reasons.add(name)
-                time.sleep(0.05)
+                time.sleep(0.02)
         except Exception as e:  # pragma: no cover
             self.err = repr(e)
 

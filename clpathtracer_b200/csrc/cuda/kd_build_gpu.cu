@@ -25,8 +25,14 @@
 // and after the last level one thread per leaf face pushes its rope down to the deepest
 // node that still covers the face (kd_build.c: push_down_link, full).
 //
-// The output is the wire format ON THE DEVICE; scene_pack_gpu.cu turns it into the
-// traversal layout without leaving the device, and CLDownloadKd hands it to a host that
+// A level is seven launches (bin, choose, three for the two scans, split = emit + scatter,
+// commit); every kernel reads the level's counts from a LevelState in device memory.  Two
+// drivers share them (clpt_gpu_build): small meshes replay ONE recorded CUDA graph of all
+// levels with capacity-sized launches and synchronise once per build; big meshes go level
+// by level with two totals read back per level to size the next one exactly.
+//
+// The output is the wire format ON THE DEVICE; the second half of this file turns it into
+// the traversal layout without leaving the device, and CLDownloadKd hands it to a host that
 // wants to look at it (the parity tests walk it with the oracle).
 #include <cuda_runtime.h>
 

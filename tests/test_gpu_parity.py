@@ -418,6 +418,17 @@ def test_clhandler_layer_and_leaf_cap(clpt, oracle, renderer, scene_cache):
         capped = oracle.render(scene, cam, 128, 96, mode=1, depth=2, max_leaf_visits=2)
         _assert_bit_equal(renderer.read_image(), capped["rgba"], "capped frame")
         assert renderer.counters() == capped["counters"] and capped["counters"]["capped"] > 0
+        # the kernel counts the rope-hop budget DOWN; the oracle counts hops up against the cap,
+        # with and without the instrumented twin (caps below 1 are refused by CLSetMaxLeafVisits)
+        for cap in (1, 3, 7):
+            L.CLSetMaxLeafVisits(cap)
+            capped = oracle.render(scene, cam, 128, 96, mode=1, depth=3, max_leaf_visits=cap)
+            for flags in (0, clpt.FLAG_COUNTERS):
+                renderer.set_params(mode=1, depth=3, flags=flags)
+                renderer.execute()
+                _assert_bit_equal(renderer.read_image(), capped["rgba"], f"cap {cap} flags {flags}")
+                if flags:
+                    assert renderer.counters() == capped["counters"]
     finally:
         L.CLSetMaxLeafVisits(4096)
         renderer.set_params()
