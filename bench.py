@@ -155,8 +155,12 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.stop_flag = index, threading.Event()
+        self.index, self.stop_flag, self.armed = index, threading.Event(), threading.Event()
         self.sm, self.reasons, self.max_mhz, self.err = [], set(), None, None
+
+    def arm(self):
+        """Start recording (the thread is started earlier: NVML takes a few hundred ms to come up)."""
+        self.armed.set()
 
     def run(self):
         try:
@@ -166,6 +170,9 @@ class ClockSampler(threading.Thread):
             h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
             while not self.stop_flag.is_set():
+                if not self.armed.is_set():
+                    time.sleep(0.002)
+                    continue
                 self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
                 mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
                 for bit, name in self.REASONS.items():
@@ -601,13 +608,14 @@ def main():
     tot = dict(zip(("rays", "splits", "leaves", "tris", "shade_vn", "capped"), [int(x) for x in totals.tolist()]))
     rays_per_frame = tot["rays"]
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(a.warmup, 3)):
         r.execute()
 
     # ---- timed: device-resident ----
-    sampler = ClockSampler(local)
-    sampler.start()
     barrier()
+    sampler.arm()
     wall0 = time.time()
     step_ms, kern_ms = [], []
     for _ in range(a.steps):

@@ -64,6 +64,10 @@ struct ClptScene {
 
 struct ClptFrame {
     float cam[16]; // row-major inverse camera matrix
+    // Per-frame constants of the camera ray (src/kernel.cl:443-449), evaluated once on the host with
+    // the same IEEE single-precision operations the kernel would repeat for every sample: the eye
+    // (column 2 of the matrix over its w) and half the image size.
+    float eye[3], half_width, half_height;
     int width, height;
     int mode, depth, spp, flags;
     int log2_sample_lanes;       // lanes per pixel = 1 << this (largest power of two <= min(spp, 32))

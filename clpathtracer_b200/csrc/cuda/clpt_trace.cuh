@@ -464,9 +464,9 @@ __device__ __forceinline__ V3 unproject(const float *M, V3 X) { // kernel.cl:89-
 __device__ __forceinline__ void primary_ray(const ClptFrame &F, int x, int y, unsigned pixel, unsigned sample,
                                             V3 &o, V3 &d) {
     const float *M = F.cam;
-    o = mk(fdiv(M[2], M[14]), fdiv(M[6], M[14]), fdiv(M[10], M[14])); // :443-445
-    float fx = fsub((float)(unsigned)x, fdiv((float)(unsigned)F.width, 2.0f));
-    float fy = fsub((float)(unsigned)y, fdiv((float)(unsigned)F.height, 2.0f));
+    o = mk(F.eye[0], F.eye[1], F.eye[2]); // :443-445, divided once per frame on the host (ClptFrame::eye)
+    float fx = fsub((float)(unsigned)x, F.half_width);
+    float fy = fsub((float)(unsigned)y, F.half_height);
     if (F.flags & CLPT_F_JITTER) {
         unsigned c[4] = { pixel, sample, 0u, 0u };
         philox(c, F.seed, CLPT_KEY1);

@@ -630,6 +630,12 @@ void clpt_state_launch_frame(int width, int height) {
 
     ClptFrame F;
     memcpy(F.cam, St.cam, sizeof(F.cam));
+    {   // (volatile: one rounded single-precision division each, never folded into something wider)
+        volatile float w = St.cam[14], ex = St.cam[2] / w, ey = St.cam[6] / w, ez = St.cam[10] / w;
+        F.eye[0] = ex, F.eye[1] = ey, F.eye[2] = ez;
+        F.half_width = (float)(unsigned)width * 0.5f;   // == width / 2.0f exactly
+        F.half_height = (float)(unsigned)height * 0.5f;
+    }
     F.width = width;
     F.height = height;
     F.mode = St.mode;

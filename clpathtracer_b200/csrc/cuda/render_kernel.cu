@@ -91,8 +91,10 @@ __device__ __forceinline__ V3 trace_sample(const ClptScene &S, const ClptFrame &
         if (depth == first_depth && aov) write_aov<COUNT>(S, F, h, o, d, x, y);
         if (h.ref < 0) break;
         const V3 nrm = hit_normal<COUNT>(S, h, o, d, cn);
-        const V3 nc = mk(fdiv(fadd(nrm.x, 1.0f), 2.0f), fdiv(fadd(nrm.y, 1.0f), 2.0f),
-                         fdiv(fadd(nrm.z, 1.0f), 2.0f));
+        // (n + 1) / 2 (:395): halving is exact in binary floating point, so the product by 0.5 is the
+        // quotient by 2 bit for bit -- and one instruction instead of an IEEE division
+        const V3 nc = mk(fmul(fadd(nrm.x, 1.0f), 0.5f), fmul(fadd(nrm.y, 1.0f), 0.5f),
+                         fmul(fadd(nrm.z, 1.0f), 0.5f));
         if (MODE == 0) return nc; // the `return` at :396
         V3 no = vadd(o, vscale(d, h.t));
         const V3 nd = vnormalize(vsub(d, vscale(nrm, fmul(2.0f, vdot(d, nrm)))));
