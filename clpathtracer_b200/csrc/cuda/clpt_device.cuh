@@ -43,6 +43,11 @@ struct ClptScene {
     const float4 *leaves;
     const float4 *tri;
     const int4 *corners;
+    // Per primitive: xyz = the flat shading normal normalize((v2-v1) x (v3-v1)) (src/kernel.cl:362),
+    // evaluated once at scene preparation with the operations the kernel would repeat at every hit;
+    // w = 0 when the primitive is flat-shaded, 1 when its first corner carries a vertex normal
+    // (the interpolated path, kernel.cl:349-360, then reads `corners` and `norms`).
+    const float4 *flat_n;
     const float4 *norms;
     const int *tri_material;
     const ClptMaterial *materials;

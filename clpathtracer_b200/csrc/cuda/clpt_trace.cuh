@@ -366,12 +366,16 @@ __device__ __forceinline__ HitDetails hit_details(const ClptScene &S, const Hit 
     return r;
 }
 
-// Shading normal of an accepted hit, kernel.cl:349-365.
+// Shading normal of an accepted hit, kernel.cl:349-365.  The flat normal is a property of the
+// primitive and comes from ClptScene::flat_n (one 16-byte load instead of two, a cross product, a
+// square root and three IEEE divisions at every hit); its w says whether the primitive is shaded
+// with interpolated vertex normals instead.
 template <bool COUNT>
 __device__ __forceinline__ V3 hit_normal(const ClptScene &S, const Hit &h, V3 o, V3 d, Counters &cn) {
     const int prim = __float_as_int(__ldg(&S.tri[3 * (size_t)h.ref].w));
-    const int4 c1 = __ldg(S.corners + 3 * (size_t)prim);
-    if (c1.y >= 0) {
+    const float4 fn = __ldg(S.flat_n + prim);
+    if (fn.w != 0.0f) {
+        const int4 c1 = __ldg(S.corners + 3 * (size_t)prim);
         const HitDetails hd = hit_details(S, h, o, d);
         const int4 c2 = __ldg(S.corners + 3 * (size_t)prim + 1);
         const int4 c3 = __ldg(S.corners + 3 * (size_t)prim + 2);
@@ -381,9 +385,7 @@ __device__ __forceinline__ V3 hit_normal(const ClptScene &S, const Hit &h, V3 o,
         if (COUNT) cn.shade_vn++;
         return vnormalize(vadd(vadd(vscale(n1, w), vscale(n2, hd.u)), vscale(n3, hd.v)));
     }
-    const V3 e1 = xyz(__ldg(S.tri + 3 * (size_t)h.ref + 1));
-    const V3 e2 = xyz(__ldg(S.tri + 3 * (size_t)h.ref + 2));
-    return vnormalize(vcross(e1, e2));
+    return xyz(fn);
 }
 
 template <bool COUNT>

@@ -132,7 +132,7 @@ struct {
     bool owns_kd = false;
 
     DevBuf<uint2> nodes;
-    DevBuf<float4> leaves, tri, norms;
+    DevBuf<float4> leaves, tri, flat_n, norms;
     DevBuf<int4> corners;
     DevBuf<int> lut;
     // device-side build (CLBuildMeshes): the mesh, the wire-format tree and its re-layout all live
@@ -239,6 +239,7 @@ void rebuild_scene_struct() {
     S.leaves = St.scene_on_gpu ? St.gpu_packed.leaves : St.leaves.ptr;
     S.tri = St.scene_on_gpu ? St.gpu_packed.tri : St.tri.ptr;
     S.corners = St.corners.ptr;
+    S.flat_n = St.scene_on_gpu ? St.gpu_packed.flat_n : St.flat_n.ptr;
     S.lut = St.scene_on_gpu ? St.gpu_packed.lut : St.lut.ptr;
     S.norms = St.norms.ptr;
     S.tri_material = St.tri_material.ptr;
@@ -267,6 +268,7 @@ void upload_scene(const kdnode *nodes, size_t node_bytes, const int *tri_indices
     St.nodes.upload(reinterpret_cast<const uint2 *>(packed.nodes.data()), packed.nodes.size(), St.stream);
     St.leaves.upload(reinterpret_cast<const float4 *>(packed.leaves.data()), packed.leaves.size(), St.stream);
     St.tri.upload(reinterpret_cast<const float4 *>(packed.tri.data()), packed.tri.size(), St.stream);
+    St.flat_n.upload(reinterpret_cast<const float4 *>(packed.flat_n.data()), packed.flat_n.size(), St.stream);
     St.corners.upload(reinterpret_cast<const int4 *>(tris), tri_bytes / sizeof(cl_int3), St.stream);
     St.lut.upload(packed.lut.data(), packed.lut.size(), St.stream);
     if (n_norms) {
@@ -873,6 +875,7 @@ void CLTerminate(void) {
     St.nodes.release();
     St.leaves.release();
     St.tri.release();
+    St.flat_n.release();
     St.norms.release();
     St.corners.release();
     St.lut.release();
@@ -884,6 +887,7 @@ void CLTerminate(void) {
         };
         drop(St.gpu_tree.wire), drop(St.gpu_tree.tri_indices);
         drop(St.gpu_packed.nodes), drop(St.gpu_packed.leaves), drop(St.gpu_packed.tri), drop(St.gpu_packed.lut);
+        drop(St.gpu_packed.flat_n);
         St.gpu_tree = ClptGpuTree();
         St.gpu_packed = ClptGpuPacked();
         St.scene_on_gpu = St.mesh_on_gpu = false;
@@ -1121,7 +1125,8 @@ size_t CLDebugReadPacked(int which, void *dst, size_t bytes) {
     case 1: src = S.leaves, have = (size_t)S.n_leaves * 4 * sizeof(float4); break;
     case 2: src = S.tri, have = (size_t)S.n_refs * 3 * sizeof(float4); break;
     case 3: src = S.lut, have = (size_t)S.lut_dim[0] * S.lut_dim[1] * S.lut_dim[2] * sizeof(int); break;
-    default: FATAL("CLDebugReadPacked: which must be 0 (nodes), 1 (leaves), 2 (triangles) or 3 (start table)");
+    case 4: src = S.flat_n, have = (size_t)S.n_prims * sizeof(float4); break;
+    default: FATAL("CLDebugReadPacked: which must be 0 (nodes), 1 (leaves), 2 (triangles), 3 (start table) or 4 (flat normals)");
     }
     if (dst && bytes >= have && have) CU(cudaMemcpy(dst, src, have, cudaMemcpyDeviceToHost));
     return have;

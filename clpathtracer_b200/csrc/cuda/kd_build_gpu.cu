@@ -1113,6 +1113,22 @@ __global__ void pack_tris_kernel(const int *__restrict__ tri_indices, int n_refs
     T[2] = make_float4(__fsub_rn(v2.x, v0.x), __fsub_rn(v2.y, v0.y), __fsub_rn(v2.z, v0.z), 0.0f);
 }
 
+// Flat shading normal per primitive (ClptScene::flat_n; the host twin is in scene_pack.cpp).
+__global__ void pack_flat_normals_kernel(const int4 *__restrict__ corners, const float4 *__restrict__ verts, int n_prims,
+                                         float4 *__restrict__ flat_n) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_prims) return;
+    const int4 c0 = corners[3 * (size_t)p];
+    const float4 v0 = verts[c0.x], v1 = verts[corners[3 * (size_t)p + 1].x], v2 = verts[corners[3 * (size_t)p + 2].x];
+    const float ax = __fsub_rn(v1.x, v0.x), ay = __fsub_rn(v1.y, v0.y), az = __fsub_rn(v1.z, v0.z);
+    const float bx = __fsub_rn(v2.x, v0.x), by = __fsub_rn(v2.y, v0.y), bz = __fsub_rn(v2.z, v0.z);
+    const float cx = __fsub_rn(__fmul_rn(ay, bz), __fmul_rn(az, by));
+    const float cy = __fsub_rn(__fmul_rn(az, bx), __fmul_rn(ax, bz));
+    const float cz = __fsub_rn(__fmul_rn(ax, by), __fmul_rn(ay, bx));
+    const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz)));
+    flat_n[p] = make_float4(__fdiv_rn(cx, len), __fdiv_rn(cy, len), __fdiv_rn(cz, len), c0.y >= 0 ? 1.0f : 0.0f);
+}
+
 struct LutGrid {
     double root_min[3], ext[3], scale[3]; // scale = (double)(float)(dim / ext), as the host packer reads it back
     int dim[3];
@@ -1167,7 +1183,6 @@ size_t g_wire_scan_cap = 0;
 
 bool clpt_gpu_pack(const ClptGpuTree &tree, const float4 *verts, const int4 *corners, int n_prims, ClptGpuPacked &out,
                    cudaStream_t s, char *err, size_t errlen) {
-    (void)n_prims;
     const int n = tree.n_nodes;
     if (n <= 0) {
         snprintf(err, errlen, "empty node array");
@@ -1201,6 +1216,11 @@ bool clpt_gpu_pack(const ClptGpuTree &tree, const float4 *verts, const int4 *cor
     pack_nodes_kernel<<<(n + T - 1) / T, T, 0, s>>>(tree.wire, n, g_wire_scan, g_new_of, out.nodes, out.leaves);
     if (tree.n_refs > 0) {
         pack_tris_kernel<<<(tree.n_refs + T - 1) / T, T, 0, s>>>(tree.tri_indices, tree.n_refs, corners, verts, out.tri);
+    }
+    ensure(out.flat_n, out.flat_n_cap, (size_t)std::max(n_prims, 1));
+    if (n_prims > 0) {
+        // (the builder has checked every corner's vertex index, tri_bounds_kernel)
+        pack_flat_normals_kernel<<<(n_prims + T - 1) / T, T, 0, s>>>(corners, verts, n_prims, out.flat_n);
     }
     // start-node table geometry: the host packer's arithmetic (scene_pack.cpp), so that both give the same table
     LutGrid G;

@@ -37,9 +37,9 @@ void clpt_gpu_build_release(void);
 // through `alloc` when too small.
 struct ClptGpuPacked {
     uint2 *nodes = nullptr;
-    float4 *leaves = nullptr, *tri = nullptr;
+    float4 *leaves = nullptr, *tri = nullptr, *flat_n = nullptr;
     int *lut = nullptr;
-    size_t nodes_cap = 0, leaves_cap = 0, tri_cap = 0, lut_cap = 0;
+    size_t nodes_cap = 0, leaves_cap = 0, tri_cap = 0, lut_cap = 0, flat_n_cap = 0;
     int n_nodes = 0, n_leaves = 0, n_refs = 0;
     float root_min[3], root_max[3];
     int lut_dim[3];

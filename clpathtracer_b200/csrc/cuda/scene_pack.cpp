@@ -248,6 +248,33 @@ bool clpt_pack_scene(const kdnode *nodes, size_t n_nodes, const int *tri_indices
         return false;
     }
     timer.lap("triangles");
+    // ---- flat shading normals, one per primitive ----
+    // normalize(e1 x e2) with e1 = v1 - v0, e2 = v2 - v0: the expressions of the kernel's V3 helpers
+    // (clpt_trace.cuh: vcross, vdot, vnormalize), one rounding per operation (-ffp-contract=off), so
+    // the stored normal is bit for bit what the kernel used to compute at every hit.
+    out.flat_n.resize(n_prims);
+#pragma omp parallel for schedule(static)
+    for (long long p = 0; p < (long long)n_prims; p++) {
+        ClptFloat4 &N = out.flat_n[(size_t)p];
+        N = ClptFloat4{ 0, 0, 0, corners[3 * (size_t)p].s[1] >= 0 ? 1.0f : 0.0f };
+        const int i0 = corners[3 * (size_t)p].s[0], i1 = corners[3 * (size_t)p + 1].s[0],
+                  i2 = corners[3 * (size_t)p + 2].s[0];
+        if (i0 < 0 || i1 < 0 || i2 < 0 || (size_t)i0 >= n_verts || (size_t)i1 >= n_verts || (size_t)i2 >= n_verts) {
+            continue; // (a primitive no leaf lists; the ones that are listed were checked above)
+        }
+        const Vector4 &v0 = verts[i0], &v1 = verts[i1], &v2 = verts[i2];
+        const float ax = v1.s[0] - v0.s[0], ay = v1.s[1] - v0.s[1], az = v1.s[2] - v0.s[2];
+        const float bx = v2.s[0] - v0.s[0], by = v2.s[1] - v0.s[1], bz = v2.s[2] - v0.s[2];
+        const float m0 = ay * bz, m1 = az * by, m2 = az * bx, m3 = ax * bz, m4 = ax * by, m5 = ay * bx;
+        const float cx = m0 - m1, cy = m2 - m3, cz = m4 - m5;
+        const float q0 = cx * cx, q1 = cy * cy, q2 = cz * cz;
+        const float s01 = q0 + q1, s012 = s01 + q2;
+        const float len = sqrtf(s012);
+        N.x = cx / len;
+        N.y = cy / len;
+        N.z = cz / len;
+    }
+    timer.lap("flat normals");
     // vertex-normal indices are dereferenced when shading.  Like the reference
     // (kernel.cl:349) only the FIRST corner decides whether normals are used, so
     // when it has one the other two must be valid as well.

@@ -61,6 +61,7 @@ struct ClptPackedScene {
     ClptStaging<ClptNode8> nodes;
     ClptStaging<ClptFloat4> leaves; // 4 per leaf
     ClptStaging<ClptFloat4> tri;    // 3 per leaf triangle slot
+    ClptStaging<ClptFloat4> flat_n; // 1 per primitive: flat normal, w = 1 if the primitive uses vertex normals
     float root_min[3], root_max[3];
     int n_nodes = 0, n_leaves = 0, n_refs = 0, n_prims = 0;
     ClptStaging<int> lut; // start-node table, lut_dim[0] fastest

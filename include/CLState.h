@@ -147,8 +147,8 @@ int CLLastBuildWasRecorded(void);
  * can cache. */
 void CLDownloadKd(kd *out);
 /* Test hook: the traversal layout in device memory, which = 0 nodes, 1 leaf records,
- * 2 triangle slots, 3 start-node table.  Returns the size in bytes; copies when dst is
- * large enough. */
+ * 2 triangle slots, 3 start-node table, 4 flat normals (one float4 per primitive).
+ * Returns the size in bytes; copies when dst is large enough. */
 size_t CLDebugReadPacked(int which, void *dst, size_t bytes);
 void CLSetMaterials(const CLMaterial *materials, size_t material_bytes,
                     const int *tri_material, size_t tri_material_bytes);

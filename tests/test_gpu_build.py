@@ -119,10 +119,10 @@ def test_device_built_tree(clpt, oracle, renderer, name, camera, mode, depth, sp
     assert np.array_equal(img.view(np.uint32), ref["rgba"].view(np.uint32))
     assert (prim >= 0).mean() > 0.01
     # device re-layout == host re-layout of the same wire arrays, byte for byte
-    dev = [renderer.read_packed(k) for k in range(4)]
+    dev = [renderer.read_packed(k) for k in range(5)]
     renderer.set_meshes(tree)  # CLSetMeshes: scene_pack.cpp
-    host = [renderer.read_packed(k) for k in range(4)]
-    for k, what in enumerate(("nodes", "leaves", "triangles", "start table")):
+    host = [renderer.read_packed(k) for k in range(5)]
+    for k, what in enumerate(("nodes", "leaves", "triangles", "start table", "flat normals")):
         assert dev[k].size == host[k].size and np.array_equal(dev[k], host[k]), what
     renderer.execute()
     assert np.array_equal(renderer.read_image().view(np.uint32), img.view(np.uint32))
